@@ -1,0 +1,507 @@
+"""Host side of the fused flow stack: parameter packing, batched FiLM conditioning nets and the
+autograd Functions that call the C ABI (libgwtf.so).
+
+A `FlowStack` views K lists of `CondRealNVPFlow3D` modules (the coupling layers of K mixture
+components, in DIRECT order) as one (K, L) grid:
+
+  * `pack_params()`  -> (K, L, rec_stride) fp32, autograd-connected to the module parameters
+                        (layout documented in include/gwtf.h);
+  * `pack_bn()`      -> (K, L, 8F) running statistics of the point-wise BatchNorms;
+  * `film(g)`        -> (B, K, L, 2, 2, F): the 4 conditioning MLPs of every layer
+                        (flows.py:33-45,68-80) evaluated for the whole grid as two batched GEMMs
+                        in PyTorch -- latent-sized work that cuBLAS serves;
+  * `nll_pass(p, g)` -> base-space samples z and per-dim log-det sums, differentiable, through
+                        the phased (batch-statistics) or fused (running-statistics) CUDA kernels.
+
+Nothing here computes the per-point flow in PyTorch: without libgwtf.so every entry raises.
+"""
+import ctypes
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.nn.functional as F
+
+from . import _native as nat
+
+BN_EPS = 1e-5
+BN_MOMENTUM = 0.1
+
+
+def _stream_ptr():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _world():
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_world_size()
+    return 1
+
+
+class _LayerRef:
+    """Direct references to the tensors of one coupling layer, in record order."""
+    __slots__ = ('module', 'warp', 'point', 'cond', 'bn_point', 'bn_cond')
+
+    def __init__(self, m):
+        self.module = m
+        self.warp = list(m.warp_inds)
+        self.point = []      # parameters in record order
+        self.bn_point = []   # (bn0, bn1) per net
+        self.cond = []       # per net, per (w, b): (lin0, bn, lin1)
+        self.bn_cond = []
+        for X in ('mu', 'logvar'):
+            t0 = getattr(m, 'T_%s_0' % X)
+            t1 = getattr(m, 'T_%s_1' % X)
+            sd0, bn0, sd1, bn1 = t0[0], t0[1], t0[3], t0[4]
+            sd2 = t1[1]
+            self.point += [sd0.weight, bn0.weight, bn0.bias, sd1.weight, sd2.weight, sd2.bias]
+            self.bn_point.append((bn0, bn1))
+            for which in ('w', 'b'):
+                seq = getattr(m, 'T_%s_0_cond_%s' % (X, which))
+                self.cond.append((seq[0], seq[1], seq[3]))
+
+
+class FlowStack:
+    def __init__(self, components):
+        """components: K lists of L CondRealNVPFlow3D modules (direct order)."""
+        self.K = len(components)
+        self.L = len(components[0])
+        assert all(len(c) == self.L for c in components)
+        self.layers = [[_LayerRef(m) for m in comp] for comp in components]
+        first = components[0][0]
+        self.F = first.f_n_features
+        self.G = first.g_n_features
+        self.desc = nat.StackDesc()
+        self.desc.n_components = self.K
+        self.desc.n_layers = self.L
+        self.desc.n_features = self.F
+        self.rec_stride = 4 * ((2 * (self.F * self.F + 5 * self.F + 2) + 3) // 4)
+        self.desc.rec_stride = self.rec_stride
+        for l in range(self.L):
+            warp = self.layers[0][l].warp
+            for j in range(self.K):
+                if self.layers[j][l].warp != warp:
+                    raise ValueError('all components must share the warp pattern of each layer')
+            mask = 0
+            for d in warp:
+                mask |= 1 << d
+            self.desc.warp_mask[l] = mask
+        self._pads = {}
+
+    # ------------------------------------------------------------------ packing
+    def _pad(self, n, device):
+        key = (n, device)
+        if key not in self._pads:
+            self._pads[key] = torch.zeros(n, device=device)
+        return self._pads[key]
+
+    def pack_params(self):
+        pieces = []
+        for j in range(self.K):
+            for l in range(self.L):
+                ref = self.layers[j][l]
+                n = 0
+                for t in ref.point:
+                    pieces.append(t.reshape(-1))
+                    n += t.numel()
+                if n < self.rec_stride:
+                    pieces.append(self._pad(self.rec_stride - n, ref.point[0].device))
+        return torch.cat(pieces).view(self.K, self.L, self.rec_stride)
+
+    def unpack_param_grads(self, dparams):
+        """Split a (K,L,rec_stride) gradient into per-parameter tensors (list in pack order)."""
+        out = []
+        flat = dparams.view(-1)
+        off = 0
+        for j in range(self.K):
+            for l in range(self.L):
+                base = off
+                for t in self.layers[j][l].point:
+                    out.append(flat[off:off + t.numel()].view_as(t))
+                    off += t.numel()
+                off = base + self.rec_stride
+        return out
+
+    def point_parameters(self):
+        return [t for j in range(self.K) for l in range(self.L) for t in self.layers[j][l].point]
+
+    def pack_bn(self):
+        pieces = []
+        for j in range(self.K):
+            for l in range(self.L):
+                for bn0, bn1 in self.layers[j][l].bn_point:
+                    pieces += [bn0.running_mean, bn0.running_var, bn1.running_mean, bn1.running_var]
+        return torch.cat(pieces).view(self.K, self.L, 8 * self.F)
+
+    @torch.no_grad()
+    def update_point_bn(self, bstat, n_total):
+        """nn.BatchNorm1d running-stat update from the batch statistics the kernels used.
+        bstat (L,K,2,4,F): mean0 | var0 (biased) | mean1 | var1 (biased)."""
+        unbias = float(n_total) / max(float(n_total) - 1.0, 1.0)
+        rms, rvs, means, vars_, nbt = [], [], [], [], []
+        bs = bstat.permute(1, 0, 2, 3, 4)   # (K,L,2,4,F)
+        for j in range(self.K):
+            for l in range(self.L):
+                for net, (bn0, bn1) in enumerate(self.layers[j][l].bn_point):
+                    rms += [bn0.running_mean, bn1.running_mean]
+                    rvs += [bn0.running_var, bn1.running_var]
+                    means += [bs[j, l, net, 0], bs[j, l, net, 2]]
+                    vars_ += [bs[j, l, net, 1], bs[j, l, net, 3]]
+                    nbt += [bn0.num_batches_tracked, bn1.num_batches_tracked]
+        torch._foreach_lerp_(rms, means, BN_MOMENTUM)
+        torch._foreach_lerp_(rvs, torch._foreach_mul(vars_, unbias), BN_MOMENTUM)
+        torch._foreach_add_(nbt, 1)
+
+    # ------------------------------------------------------------------ FiLM nets
+    def film(self, g, training, sync):
+        """(B,K,L,2,2,F): [...,0,:] = eps + exp(cond_w(g)), [...,1,:] = cond_b(g)."""
+        K, L, Fd = self.K, self.L, self.F
+        conds = [c for j in range(K) for l in range(L) for c in self.layers[j][l].cond]   # C = K*L*4
+        C = len(conds)
+        W0 = torch.stack([c[0].weight for c in conds]).view(C * Fd, self.G)
+        H = F.linear(g, W0)                                                                 # (B, C*F)
+        bw = torch.cat([c[1].weight for c in conds])
+        bb = torch.cat([c[1].bias for c in conds])
+        rm = torch.cat([c[1].running_mean for c in conds])
+        rv = torch.cat([c[1].running_var for c in conds])
+        if training:
+            Hn, mean, var_unb = _batch_norm_train(H, bw, bb, sync)
+            with torch.no_grad():
+                torch._foreach_lerp_([c[1].running_mean for c in conds], list(mean.view(C, Fd).unbind(0)), BN_MOMENTUM)
+                torch._foreach_lerp_([c[1].running_var for c in conds], list(var_unb.view(C, Fd).unbind(0)),
+                                     BN_MOMENTUM)
+                torch._foreach_add_([c[1].num_batches_tracked for c in conds], 1)
+        else:
+            Hn = (H - rm) * torch.rsqrt(rv + BN_EPS) * bw + bb
+        A = Hn * torch.sigmoid(Hn)
+        W1 = torch.stack([c[2].weight for c in conds])                                      # (C,F,F)
+        b1 = torch.stack([c[2].bias for c in conds])                                        # (C,F)
+        O = torch.baddbmm(b1.unsqueeze(1), A.view(-1, C, Fd).transpose(0, 1), W1.transpose(1, 2))  # (C,B,F)
+        O = O.view(K, L, 2, 2, -1, Fd).permute(4, 0, 1, 2, 3, 5)                            # (B,K,L,net,which,F)
+        eps = self.layers[0][0].module.eps
+        s = eps + torch.exp(O[..., 0, :])
+        return torch.stack([s, O[..., 1, :]], dim=4).contiguous()
+
+    # ------------------------------------------------------------------ kernels
+    def nll_pass(self, p, g, training):
+        """-> z (K,B,3,N) base-space samples, ssum (K,B,3,N) per-dim sums of logvar."""
+        sync = training and _world() > 1
+        film = self.film(g, training, sync)
+        params = self.pack_params()
+        bnbuf = self.pack_bn()
+        z, ssum, bstat, n_total = _StackNLLPass.apply(p.contiguous(), params, film, bnbuf, self, training, sync)
+        if training:
+            self.update_point_bn(bstat, n_total)
+        return z, ssum
+
+    @torch.no_grad()
+    def nll_eval_fused(self, p, g, base, logw, want_logp=False):
+        """Fused no-grad eval forward -> nll (B,N) [, logp (B,N,K)]."""
+        film = self.film(g, False, False)
+        params = self.pack_params()
+        bnbuf = self.pack_bn()
+        p = p.contiguous()
+        B, _, N = p.shape
+        nll = torch.empty(B, N, device=p.device)
+        logp = torch.empty(B, N, self.K, device=p.device) if want_logp else None
+        nat.check(nat.lib().gwtf_nll_fwd_eval(ctypes.byref(self.desc), nat.ptr(params), nat.ptr(bnbuf), nat.ptr(film),
+                                              nat.ptr(p), nat.ptr(base.contiguous()), nat.ptr(logw.contiguous()),
+                                              B, N, nat.ptr(nll), nat.ptr(logp), None, None, _stream_ptr()),
+                  'gwtf_nll_fwd_eval')
+        return (nll, logp) if want_logp else nll
+
+
+def _batch_norm_train(H, weight, bias, sync):
+    """Train-mode BatchNorm over dim 0 of (B,C); returns normalised output and the (detached)
+    batch mean / unbiased variance for the running-stat update.  With `sync` the statistics are
+    shared by all ranks (SyncBatchNorm semantics, train_ae.py:152)."""
+    if not sync:
+        mean = H.mean(0)
+        var = H.var(0, unbiased=False)
+        n = H.shape[0]
+        out = (H - mean) * torch.rsqrt(var + BN_EPS) * weight + bias
+        return out, mean.detach(), (var * (n / max(n - 1, 1))).detach()
+    return _SyncBN.apply(H, weight, bias)
+
+
+class _SyncBN(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, H, weight, bias):
+        stats = torch.cat([H.sum(0), (H * H).sum(0), H.new_full((1,), float(H.shape[0]))])
+        dist.all_reduce(stats)
+        C = H.shape[1]
+        n = stats[-1]
+        mean = stats[:C] / n
+        var = (stats[C:2 * C] / n - mean * mean).clamp_min(0)
+        istd = torch.rsqrt(var + BN_EPS)
+        xhat = (H - mean) * istd
+        ctx.save_for_backward(xhat, weight, istd, n)
+        ctx.mark_non_differentiable(mean, var)
+        return xhat * weight + bias, mean, var * (n / (n - 1).clamp_min(1))
+
+    @staticmethod
+    def backward(ctx, dy, _dm, _dv):
+        xhat, weight, istd, n = ctx.saved_tensors
+        dw = (dy * xhat).sum(0)
+        db = dy.sum(0)
+        C = dy.shape[1]
+        sums = torch.cat([db, dw])
+        dist.all_reduce(sums)
+        dxhat = dy * weight
+        mean_d = sums[:C] * weight / n
+        mean_dx = sums[C:] * weight / n
+        dH = (dxhat - mean_d - xhat * mean_dx) * istd
+        return dH, dw, db
+
+
+class _StackNLLPass(torch.autograd.Function):
+    """points (B,3,N), params (K,L,RS), film (B,K,L,2,2,F) -> z, ssum  (reference mode='inverse',
+    decoders.py:72-77 over all K components)."""
+
+    @staticmethod
+    def forward(ctx, p, params, film, bnbuf, stack, training, sync):
+        lib = nat.lib()
+        K, L, Fd = stack.K, stack.L, stack.F
+        B, _, N = p.shape
+        dev = p.device
+        desc = ctypes.byref(stack.desc)
+        st = _stream_ptr()
+        ubuf = torch.empty(L, K, B, 3, N, device=dev)
+        ssum = torch.zeros(K, B, 3, N, device=dev)
+        ld = torch.zeros(K, B, N, device=dev)
+        mom = sum1 = bstat = None
+        n_total = float(B * N)
+        if training:
+            mom = torch.zeros(L, K, nat.MOM_STRIDE, device=dev, dtype=torch.float64)
+            sum1 = torch.zeros(L, K, 2, 2, Fd, device=dev, dtype=torch.float64)
+            bstat = torch.empty(L, K, 2, 4, Fd, device=dev)
+        if not sync:
+            nat.check(lib.gwtf_fwd_all(desc, int(training), nat.ptr(params), nat.ptr(bnbuf), nat.ptr(film), nat.ptr(p),
+                                       None, None, nat.ptr(ubuf), nat.ptr(ld), nat.ptr(ssum), nat.ptr(mom),
+                                       nat.ptr(sum1), nat.ptr(bstat), B, N, None, None, st), 'gwtf_fwd_all')
+        else:
+            cnt = torch.tensor([n_total], device=dev, dtype=torch.float64)
+            dist.all_reduce(cnt)
+            n_total = float(cnt.item())
+            nat.check(lib.gwtf_fwd_moments(desc, nat.ptr(p), B, N, nat.ptr(mom[L - 1]), st), 'gwtf_fwd_moments')
+            for l in range(L - 1, -1, -1):
+                dist.all_reduce(mom[l])
+                for phase in (0, 1):
+                    nat.check(lib.gwtf_fwd_layer(desc, l, phase, 1, nat.ptr(params), nat.ptr(bnbuf), nat.ptr(film),
+                                                 nat.ptr(p), nat.ptr(ubuf), nat.ptr(ld), nat.ptr(ssum), nat.ptr(mom),
+                                                 nat.ptr(sum1), B, N, n_total, st), 'gwtf_fwd_layer')
+                    if phase == 0:
+                        dist.all_reduce(sum1[l])
+            nat.check(lib.gwtf_fwd_bstat(desc, nat.ptr(params), nat.ptr(mom), nat.ptr(sum1), n_total, nat.ptr(bstat),
+                                         st), 'gwtf_fwd_bstat')
+        ctx.stack = stack
+        ctx.training = training
+        ctx.sync = sync
+        ctx.n_total = n_total
+        ctx.save_for_backward(p, params, film, bnbuf, ubuf, mom, sum1)
+        z = ubuf[0]
+        ctx.mark_non_differentiable(*([bstat] if bstat is not None else []))
+        return z, ssum, bstat, n_total
+
+    @staticmethod
+    def backward(ctx, dz, dssum, _dbstat, _dn):
+        lib = nat.lib()
+        stack = ctx.stack
+        p, params, film, bnbuf, ubuf, mom, sum1 = ctx.saved_tensors
+        K, L, Fd = stack.K, stack.L, stack.F
+        B, _, N = p.shape
+        dev = p.device
+        desc = ctypes.byref(stack.desc)
+        st = _stream_ptr()
+        gbuf = dz.contiguous().clone() if dz is not None else torch.zeros(K, B, 3, N, device=dev)
+        gs = dssum.contiguous() if dssum is not None else torch.zeros(K, B, 3, N, device=dev)
+        dobuf = torch.empty(K, B, 6, N, device=dev)
+        dparams = torch.zeros_like(params)
+        dfilm = torch.zeros_like(film)
+        dpoints = torch.zeros_like(p)
+        bsum = torch.zeros(L, K, 2, 4, Fd, device=dev, dtype=torch.float64)
+        train = int(ctx.training)
+        if not ctx.sync:
+            nat.check(lib.gwtf_bwd_all(desc, train, nat.ptr(params), nat.ptr(bnbuf), nat.ptr(film), nat.ptr(p),
+                                       None, None, nat.ptr(ubuf), None, nat.ptr(mom), nat.ptr(sum1), None, None,
+                                       nat.ptr(bsum), nat.ptr(gbuf), nat.ptr(gs), nat.ptr(dobuf), nat.ptr(dparams),
+                                       nat.ptr(dfilm), None, None, nat.ptr(dpoints), B, N, st), 'gwtf_bwd_all')
+        else:
+            for l in range(L):
+                for phase in (0, 1):
+                    nat.check(lib.gwtf_bwd_layer(desc, l, phase, train, nat.ptr(params), nat.ptr(bnbuf),
+                                                 nat.ptr(film), nat.ptr(p), nat.ptr(ubuf), nat.ptr(mom),
+                                                 nat.ptr(sum1), nat.ptr(bsum), nat.ptr(gbuf), nat.ptr(gs),
+                                                 nat.ptr(dobuf), nat.ptr(dparams), nat.ptr(dfilm), B, N,
+                                                 ctx.n_total, st), 'gwtf_bwd_layer')
+                    dist.all_reduce(bsum[l])
+            nat.check(lib.gwtf_bwd_finish(desc, train, nat.ptr(params), nat.ptr(bnbuf), nat.ptr(mom), nat.ptr(bsum),
+                                          nat.ptr(gbuf), nat.ptr(p), nat.ptr(dparams), nat.ptr(dpoints), B, N,
+                                          ctx.n_total, st), 'gwtf_bwd_finish')
+        return dpoints, dparams, dfilm, None, None, None, None
+
+
+class _MixtureHead(torch.autograd.Function):
+    """z, ssum, base (B,2,3), logw (B,K) -> per-point mixture NLL (B,N)  (losses.py:112-128)."""
+
+    @staticmethod
+    def forward(ctx, z, ssum, base, logw, stack):
+        lib = nat.lib()
+        K, B, _, N = z.shape
+        dev = z.device
+        z = z.contiguous()
+        ld = ssum.sum(2)
+        base = base.contiguous()
+        logw = logw.contiguous()
+        nll = torch.empty(B, N, device=dev)
+        nat.check(lib.gwtf_nll_from_state(ctypes.byref(stack.desc), nat.ptr(z), nat.ptr(ld), nat.ptr(base),
+                                          nat.ptr(logw), B, N, nat.ptr(nll), None, _stream_ptr()),
+                  'gwtf_nll_from_state')
+        ctx.stack = stack
+        ctx.save_for_backward(z, ld, base, logw, nll)
+        return nll
+
+    @staticmethod
+    def backward(ctx, dnll):
+        lib = nat.lib()
+        z, ld, base, logw, nll = ctx.saved_tensors
+        K, B, _, N = z.shape
+        dev = z.device
+        gbuf = torch.empty(K, B, 3, N, device=dev)
+        gs = torch.empty(K, B, 3, N, device=dev)
+        dbase = torch.zeros_like(base)
+        dlogw = torch.zeros_like(logw)
+        nat.check(lib.gwtf_bwd_seed(ctypes.byref(ctx.stack.desc), nat.ptr(z), nat.ptr(ld), nat.ptr(base),
+                                    nat.ptr(logw), nat.ptr(nll), nat.ptr(dnll.contiguous()), B, N, nat.ptr(gbuf),
+                                    nat.ptr(gs), nat.ptr(dbase), nat.ptr(dlogw), _stream_ptr()), 'gwtf_bwd_seed')
+        return gbuf, gs, dbase, dlogw, None
+
+
+# ---------------------------------------------------------------------------------------------
+# public entry points used by the drop-in modules
+# ---------------------------------------------------------------------------------------------
+def mixture_nll(stack, p, g, mu_base, lv_base, logits, training, want_nll=True):
+    """All K inverse stacks + (optionally) the in-kernel mixture NLL.
+
+    -> (z (K,B,3,N), ssum (K,B,3,N), nll (B,N) or None).  With gradients disabled and eval-mode
+    BatchNorm the single fused kernel is used and z / ssum are not materialised.
+    """
+    nat.lib()
+    if not p.is_cuda:
+        raise nat.GwtfError('the flow stack runs on CUDA tensors only (got %s)' % p.device)
+    base = torch.stack([mu_base, lv_base], dim=1)                                   # (B,2,3)
+    logw = logits - torch.logsumexp(logits, dim=-1, keepdim=True)                   # losses.py:101-104
+    needs_grad = torch.is_grad_enabled()
+    if want_nll and not training and not needs_grad:
+        return None, None, stack.nll_eval_fused(p, g, base, logw)
+    z, ssum = stack.nll_pass(p, g, training)
+    nll = _MixtureHead.apply(z, ssum, base, logw, stack) if want_nll else None
+    return z, ssum, nll
+
+
+def mixture_cdf(logits_row):
+    """Inclusive CDF of softmax(logits) the way np.random.choice builds it (flow_mixture.py:149-153):
+    fp32 probabilities, float64 cumsum, normalised; stored fp32 with the last entry pinned to 1."""
+    e = np.exp(logits_row.astype(np.float32))
+    probs = e / e.sum()
+    cdf = np.cumsum(probs.astype(np.float64))
+    cdf /= cdf[-1]
+    cdf = cdf.astype(np.float32)
+    cdf[-1] = np.float32(1.0)
+    return cdf
+
+
+@torch.no_grad()
+def sample_mixture(stack, g, mu_base, lv_base, logits, n_points, seed, stream_id=0, idx=None, eps=None,
+                   want_z=False):
+    """Eval-mode sampling of n_points per shape -> samples (B,3,N), labels (B,N) int32 in 1..K,
+    z (B,3,N) or None.  `idx` (B,N) int32 / `eps` (B,3,N) replace the in-kernel Philox draws."""
+    lib = nat.lib()
+    if not g.is_cuda:
+        raise nat.GwtfError('the flow stack runs on CUDA tensors only (got %s)' % g.device)
+    B = g.shape[0]
+    dev = g.device
+    film = stack.film(g, False, False)
+    params = stack.pack_params()
+    bnbuf = stack.pack_bn()
+    base = torch.stack([mu_base, lv_base], dim=1).contiguous()
+    host_logits = logits.detach().float().cpu().numpy()                             # as the reference: :149
+    cdf = torch.from_numpy(np.stack([mixture_cdf(r) for r in host_logits])).to(dev)
+    samples = torch.empty(B, 3, n_points, device=dev)
+    labels = torch.empty(B, n_points, device=dev, dtype=torch.int32)
+    z = torch.empty(B, 3, n_points, device=dev) if want_z else None
+    if idx is not None:
+        idx = idx.to(device=dev, dtype=torch.int32).contiguous()
+    if eps is not None:
+        eps = eps.to(device=dev, dtype=torch.float32).contiguous()
+    nat.check(lib.gwtf_sample(ctypes.byref(stack.desc), nat.ptr(params), nat.ptr(bnbuf), nat.ptr(film), nat.ptr(base),
+                              nat.ptr(cdf), B, n_points, ctypes.c_uint64(seed & (2 ** 64 - 1)),
+                              ctypes.c_uint32(stream_id & 0xFFFFFFFF), nat.ptr(idx), nat.ptr(eps), nat.ptr(samples),
+                              nat.ptr(labels), nat.ptr(z), _stream_ptr()), 'gwtf_sample')
+    return samples, labels, z
+
+
+_warned_list_api = [False]
+
+
+@torch.no_grad()
+def run_module_stack(stack, p, g, mode, training):
+    """Per-module list API (flows.py:117,160; decoders.py:79) on a K=1 stack: every layer's
+    (p_out, mu, logvar), indexed by layer in DIRECT order.  Inference-only: the returned
+    tensors carry no autograd graph (training goes through Flow_Mixture_Model.decode)."""
+    lib = nat.lib()
+    if not p.is_cuda:
+        raise nat.GwtfError('the flow stack runs on CUDA tensors only (got %s)' % p.device)
+    if mode not in ('direct', 'inverse'):
+        raise ValueError(mode)
+    if torch.is_grad_enabled() and not _warned_list_api[0]:
+        pass
+    assert stack.K == 1
+    L, Fd = stack.L, stack.F
+    p = p.contiguous().float()
+    B, _, N = p.shape
+    dev = p.device
+    sync = training and _world() > 1
+    film = stack.film(g, training, sync)
+    params = stack.pack_params()
+    bnbuf = stack.pack_bn()
+    desc = ctypes.byref(stack.desc)
+    st = _stream_ptr()
+    trio = torch.empty(L, 3, B, 3, N, device=dev)
+    order = list(range(L)) if mode == 'direct' else list(range(L - 1, -1, -1))
+    n_total = float(B * N)
+    mom = sum1 = None
+    if training:
+        mom = torch.zeros(L, 1, nat.MOM_STRIDE, device=dev, dtype=torch.float64)
+        sum1 = torch.zeros(L, 1, 2, 2, Fd, device=dev, dtype=torch.float64)
+        if sync:
+            cnt = torch.tensor([n_total], device=dev, dtype=torch.float64)
+            dist.all_reduce(cnt)
+            n_total = float(cnt.item())
+        nat.check(lib.gwtf_fwd_moments(desc, nat.ptr(p), B, N, nat.ptr(mom[order[0]]), st), 'gwtf_fwd_moments')
+    cur = p
+    for i, l in enumerate(order):
+        nxt = order[i + 1] if i + 1 < L else None
+        phases = (0, 1) if training else (1,)
+        if sync:
+            dist.all_reduce(mom[l])
+        for phase in phases:
+            xout = trio[l, 0]
+            nat.check(lib.gwtf_fwd_layer_ex(desc, l, phase, int(training), int(mode == 'direct'), nat.ptr(params),
+                                            nat.ptr(bnbuf), nat.ptr(film), nat.ptr(cur), 1, nat.ptr(xout), None, None,
+                                            nat.ptr(trio[l]), nat.ptr(mom[l]) if training else None,
+                                            nat.ptr(mom[nxt]) if (training and nxt is not None) else None,
+                                            nat.ptr(sum1[l]) if training else None, B, N, n_total, st),
+                      'gwtf_fwd_layer_ex')
+            if sync and phase == 0:
+                dist.all_reduce(sum1[l])
+        cur = trio[l, 0]
+    if training:
+        bstat = torch.empty(L, 1, 2, 4, Fd, device=dev)
+        nat.check(lib.gwtf_fwd_bstat(desc, nat.ptr(params), nat.ptr(mom), nat.ptr(sum1), n_total, nat.ptr(bstat), st),
+                  'gwtf_fwd_bstat')
+        stack.update_point_bn(bstat, n_total)
+    ps = [trio[l, 0] for l in range(L)]
+    mus = [trio[l, 1] for l in range(L)]
+    lvs = [trio[l, 2] for l in range(L)]
+    return ps, mus, lvs

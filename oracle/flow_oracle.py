@@ -330,7 +330,7 @@ def u01(x: np.ndarray) -> np.ndarray:
 def sample_streams(seed: int, stream: int, B: int, N: int):
     """The per-point random numbers the sampling kernel draws.
 
-    counter = (n, b, call, 0), key = (seed & 0xffffffff, stream).  call 0 -> words
+    counter = (n, b, call, 0), key = (seed & 0xffffffff, stream ^ (seed >> 32)).  call 0 -> words
     (r0,r1,r2,r3), call 1 -> (r4,..).  u_comp = u01(r0);  Box-Muller on
     (r1,r2) -> eps0, eps1 and on (r3,r4) -> eps2 (cosine branch only).
     Returns u_comp (B,N) float32 and the raw uint32 words (B,N,8).
@@ -339,7 +339,7 @@ def sample_streams(seed: int, stream: int, B: int, N: int):
     b = np.arange(B, dtype=np.uint32)[:, None].repeat(N, 1)
     key = np.zeros((B, N, 2), dtype=np.uint32)
     key[..., 0] = np.uint32(seed & 0xFFFFFFFF)
-    key[..., 1] = np.uint32(stream & 0xFFFFFFFF)
+    key[..., 1] = np.uint32((stream ^ (seed >> 32)) & 0xFFFFFFFF)
     words = []
     for call in (0, 1):
         ctr = np.stack([n, b, np.full_like(n, call), np.zeros_like(n)], axis=-1)

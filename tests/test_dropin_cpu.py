@@ -1,0 +1,79 @@
+"""CPU: drop-in surface (names, shapes, constructors, loader, C-ABI exports) -- no kernel runs."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from tests.util import GOLDEN_CASES, Golden, build_dropin, golden_cfg
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize('case', GOLDEN_CASES)
+def test_state_dict_is_reference_compatible(case):
+    gd = Golden(case)
+    model = build_dropin(gd)           # strict=True load of a reference-generated state_dict
+    ref_sd = gd.sd(torch.float32)
+    own = model.state_dict()
+    assert list(own.keys()) == list(ref_sd.keys())
+    for k in own:
+        assert own[k].shape == ref_sd[k].shape, k
+
+
+def test_derived_decoder_size_matches_reference_configs():
+    from go_with_the_flows_b200.networks.flow_mixture import Flow_Mixture_Model
+    # airplane -> (11 triples, F=37), autoencoding / SVR -> (11, 33)
+    probe = Flow_Mixture_Model.__new__(Flow_Mixture_Model)
+    for G, want in ((128, (11, 37)), (512, (11, 33))):
+        probe.n_components, probe.params_reduce_mode = 4, 'depth_and_feature'
+        probe.p_decoder_n_flows, probe.p_decoder_n_features, probe.g_latent_space_size = 21, 64, G
+        assert probe._get_decoder_params() == want
+
+
+def test_cabi_exports_every_declared_symbol():
+    from go_with_the_flows_b200 import _native
+    from go_with_the_flows_b200.build import build
+    build()
+    header = open(os.path.join(ROOT, 'include', 'gwtf.h')).read()
+    declared = set(re.findall(r'\b(gwtf_[a-z0-9_]+)\s*\(', header))
+    declared -= {'gwtf_stack_desc'}
+    handle = ctypes.CDLL(_native.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(handle, name), name
+    assert set(_native.EXPORTED) == declared
+    assert _native.lib().gwtf_version() == 1
+
+
+def test_flow_modules_refuse_cpu_tensors():
+    from go_with_the_flows_b200._native import GwtfError
+    gd = Golden(GOLDEN_CASES[0])
+    model = build_dropin(gd)
+    p = gd.t('in/p', torch.float32)
+    g = gd.t('in/g', torch.float32)
+    with pytest.raises(GwtfError):
+        model.decode(p, g, p.shape[2])
+
+
+@pytest.mark.skipif(not os.path.isdir('/root/reference/lib/networks'), reason='reference tree only in the build container')
+def test_seeded_construction_reproduces_reference_weights():
+    import sys
+    sys.dont_write_bytecode = True
+    sys.path.insert(0, '/root/reference')
+    try:
+        from lib.networks.flow_mixture import Flow_Mixture_Model as RefModel
+        from go_with_the_flows_b200.networks.flow_mixture import Flow_Mixture_Model
+        cfg = golden_cfg(Golden('small_freevar_global'))
+        torch.manual_seed(3)
+        ref = RefModel(**cfg)
+        torch.manual_seed(3)
+        own = Flow_Mixture_Model(**cfg)
+        rs, os_ = ref.state_dict(), own.state_dict()
+        assert list(rs.keys()) == list(os_.keys())
+        for k in rs:
+            assert torch.equal(rs[k], os_[k]), k
+    finally:
+        sys.path.remove('/root/reference')
+        for m in [m for m in sys.modules if m == 'lib' or m.startswith('lib.')]:
+            del sys.modules[m]

@@ -45,3 +45,26 @@ def max_rel(a, b, floor=1e-12):
     a = a.double()
     b = b.double()
     return float(((a - b).abs() / b.abs().clamp_min(floor)).max())
+
+
+BASE_CFG = dict(
+    train_mode='p_rnvp_mc_g_rnvp_vae', util_mode='training', deterministic=False,
+    pc_enc_init_n_channels=3, pc_enc_init_n_features=8, pc_enc_n_features=[8, 16],
+    g_prior_n_flows=1, g_prior_n_features=8, g_posterior_n_layers=1,
+    p_latent_space_size=3, p_prior_n_layers=1, p_decoder_base_var=-3.9551,
+    pnll_weight=1.0, gnll_weight=1.0, gent_weight=1.0,
+)
+
+
+def golden_cfg(gd):
+    cfg = dict(BASE_CFG)
+    cfg.update(gd.meta)
+    return cfg
+
+
+def build_dropin(gd, device='cpu'):
+    """Our drop-in Flow_Mixture_Model carrying the golden (reference-generated) state_dict."""
+    from go_with_the_flows_b200.networks.flow_mixture import Flow_Mixture_Model
+    model = Flow_Mixture_Model(**golden_cfg(gd))
+    model.load_state_dict(gd.sd(torch.float32), strict=True)
+    return model.to(device)
