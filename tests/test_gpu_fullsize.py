@@ -1,0 +1,99 @@
+"""GPU parity at BASELINE.json configs[0] size (C1): airplane model at random init, 4 clouds x 2048
+points, against the CPU oracle in fp64; plus size-independent properties at the C2 batch."""
+import pytest
+import torch
+
+from oracle import flow_oracle as fo
+from tests.util import max_rel, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+def _model(cfg_name='generative'):
+    from go_with_the_flows_b200 import configs
+    from go_with_the_flows_b200.networks.flow_mixture import Flow_Mixture_Model
+    cfg = dict(configs.BY_NAME[cfg_name])
+    torch.manual_seed(0)
+    return cfg, Flow_Mixture_Model(**cfg)
+
+
+def _inputs(B, N, G):
+    gen = torch.Generator().manual_seed(1234)
+    p = 0.2 * torch.randn(B, 3, N, generator=gen)
+    gen = torch.Generator().manual_seed(4321)
+    g = 0.5 * torch.randn(B, G, generator=gen)
+    return p, g
+
+
+def _oracle(sd, cfg, p, g, training, dtype):
+    sd = {k: (v.detach().clone().to(dtype) if v.is_floating_point() else v.clone()) for k, v in sd.items()}
+    for k, v in sd.items():
+        if v.is_floating_point() and k.startswith('pc_decoder') and 'running' not in k and not k.endswith('eps'):
+            v.requires_grad_(True)
+    p = p.to(dtype).requires_grad_(True)
+    g = g.to(dtype).requires_grad_(True)
+    out = fo.mixture_nll(p, g, sd, base_type=cfg['p_decoder_base_type'], weights_type=cfg['weights_type'],
+                         training=training, base_var=cfg['p_decoder_base_var'])
+    out['pnll'].backward()
+    return out, p.grad, g.grad, sd
+
+
+def _grad_err(named, sd, key_filter):
+    num = den = 0.0
+    for k, v in sd.items():
+        if not key_filter(k) or not v.requires_grad:
+            continue
+        ref = v.grad.double()
+        got = named[k] if torch.is_tensor(named[k]) else named[k]
+        num += float((got.double() - ref).pow(2).sum())
+        den += float(ref.pow(2).sum())
+    return (num / den) ** 0.5
+
+
+@pytest.mark.parametrize('training', [False, True])
+def test_c1_airplane_4x2048_against_fp64_oracle(training):
+    from go_with_the_flows_b200.networks.losses import FlowMixtureNLL
+    cfg, model = _model()
+    sd0 = {k: v.clone() for k, v in model.state_dict().items()}
+    p, g = _inputs(4, 2048, cfg['g_latent_space_size'])
+    want, dp64, dg64, sd64 = _oracle(sd0, cfg, p, g, training, torch.float64)
+    w32, dp32, dg32, sd32 = _oracle(sd0, cfg, p, g, training, torch.float32)
+    model = model.cuda()
+    model.mode = 'training'
+    model.train(training)
+    pc = p.cuda().requires_grad_(True)
+    gc = g.cuda().requires_grad_(True)
+    out, logits = model.decode(pc, gc, 2048)
+    nll = out[0]['mixture_nll']
+    FlowMixtureNLL()(out, logits).backward()
+    # per-point log-likelihood: 1e-4 relative (north star); the reference's own fp32 noise is ~3e-7
+    assert max_rel(nll.detach().cpu(), want['nll']) < 1e-4
+    # gradients: norm-wise against fp64 with the fp32 oracle as yardstick
+    noise_dp, noise_dg = rel_l2(dp32, dp64), rel_l2(dg32, dg64)
+    assert rel_l2(pc.grad.cpu(), dp64) < max(1e-4, 3 * noise_dp)
+    assert rel_l2(gc.grad.cpu(), dg64) < max(1e-4, 3 * noise_dg)
+    named = {k: v.grad.detach().cpu() for k, v in model.named_parameters() if v.grad is not None}
+    is_dec = lambda k: k.startswith('pc_decoder') and k in named   # noqa: E731
+    ours = _grad_err(named, sd64, is_dec)
+    noise = _grad_err({k: v.grad for k, v in sd32.items() if v.requires_grad and v.grad is not None}, sd64, is_dec)
+    assert ours < max(1e-4, 3 * noise), (ours, noise)
+
+
+def test_c2_batch_properties():
+    """64 x 2048 (the bench batch): eval-mode fused kernel == phased path; NLL of a permuted cloud is
+    the permuted NLL (points are independent in eval mode); loss finite."""
+    cfg, model = _model()
+    model = model.cuda().eval()
+    model.mode = 'training'
+    p, g = _inputs(64, 2048, cfg['g_latent_space_size'])
+    p, g = p.cuda(), g.cuda()
+    with torch.no_grad():
+        fused = model.decode(p, g, 2048)[0][0]['mixture_nll']
+    with torch.enable_grad():
+        phased = model.decode(p, g.clone().requires_grad_(True), 2048)[0][0]['mixture_nll'].detach()
+    assert torch.isfinite(fused).all()
+    assert max_rel(fused.cpu(), phased.cpu()) < 1e-5
+    perm = torch.randperm(2048, device='cuda')
+    with torch.no_grad():
+        shuffled = model.decode(p[:, :, perm].contiguous(), g, 2048)[0][0]['mixture_nll']
+    assert max_rel(shuffled.cpu(), fused[:, perm].cpu()) < 1e-5
