@@ -30,8 +30,8 @@ def _oracle(sd, cfg, p, g, training, dtype):
     for k, v in sd.items():
         if v.is_floating_point() and k.startswith('pc_decoder') and 'running' not in k and not k.endswith('eps'):
             v.requires_grad_(True)
-    p = p.to(dtype).requires_grad_(True)
-    g = g.to(dtype).requires_grad_(True)
+    p = p.detach().clone().to(dtype).requires_grad_(True)
+    g = g.detach().clone().to(dtype).requires_grad_(True)
     out = fo.mixture_nll(p, g, sd, base_type=cfg['p_decoder_base_type'], weights_type=cfg['weights_type'],
                          training=training, base_var=cfg['p_decoder_base_var'])
     out['pnll'].backward()
