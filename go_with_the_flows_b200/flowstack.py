@@ -61,9 +61,53 @@ class _LayerRef:
                 self.cond.append((seq[0], seq[1], seq[3]))
 
 
+class _Master:
+    """One flat leaf tensor that backs many module parameters (or buffers) as views."""
+
+    def __init__(self, name, shape, dtype=torch.float32):
+        self.name = name
+        self.shape = shape
+        self.dtype = dtype
+        self.tensor = None
+        self.members = []      # (owner module, attribute name, is_param, offset, shape)
+        self.grad_views = None
+        self.grad_ptr = None
+        self.params = None     # Parameter objects of the members (grad masters only)
+
+    def add(self, owner, attr, is_param, offset, shape):
+        self.members.append((owner, attr, is_param, offset, tuple(shape)))
+
+    def current(self, m):
+        owner, attr, is_param, _, _ = m
+        return owner._parameters[attr] if is_param else owner._buffers[attr]
+
+
 class FlowStack:
-    def __init__(self, components):
-        """components: K lists of L CondRealNVPFlow3D modules (direct order)."""
+    """K x L grid of coupling layers whose tensors live in a few flat 'master' tensors.
+
+    The module Parameters / buffers keep their identity, names and shapes (state_dict, optimizers
+    and checkpoints see nothing new) but their storage is a view into a master laid out the way
+    the kernels read it, so packing is free and autograd runs on 6 leaves instead of ~4,800:
+
+      point   (K, L, rec_stride)   sd0 / bn0 affine / sd1 / sd2 of both nets   (kernel `params`)
+      bn      (K, L, 8F)           running stats of the point-wise BatchNorms   (kernel `bnbuf`)
+      c_w0    (C, F, G)            first Linear of the C = K*L*4 FiLM nets
+      c_bnw, c_bnb (C, F)          their BatchNorm affine;  c_rm, c_rv (C, F) running stats
+      c_w1    (C, F, F), c_b1 (C, F)   second Linear
+      nbt     (n,) int64           every num_batches_tracked counter
+
+    Gradients: autograd accumulates into `master.grad`; after each backward the Parameters' `.grad`
+    are (re)attached as views of it.  Because DistributedDataParallel never sees the masters, the
+    decoder gradients are averaged across ranks here (one all-reduce per master, issued from the
+    backward pass) whenever a process group is initialised -- the reference's bucketed DDP
+    all-reduce (train_ae.py:153) for these tensors, as a single flat buffer.
+    """
+
+    def __init__(self, components, own_storage=True):
+        """components: K lists of L CondRealNVPFlow3D modules (direct order).  own_storage=False
+        (the per-module list API) leaves the module tensors where they are and gathers them per
+        call instead -- only one stack may own the storage of a given set of modules."""
+        self.flat = own_storage
         self.K = len(components)
         self.L = len(components[0])
         assert all(len(c) == self.L for c in components)
@@ -86,46 +130,164 @@ class FlowStack:
             for d in warp:
                 mask |= 1 << d
             self.desc.warp_mask[l] = mask
-        self._pads = {}
+        self.sync_gradients = True
+        self.C = self.K * self.L * 4
+        if self.flat:
+            self._build_layout()
 
-    # ------------------------------------------------------------------ packing
-    def _pad(self, n, device):
-        key = (n, device)
-        if key not in self._pads:
-            self._pads[key] = torch.zeros(n, device=device)
-        return self._pads[key]
+    # ------------------------------------------------------------------ flat storage
+    def _build_layout(self):
+        K, L, Fd, G = self.K, self.L, self.F, self.G
+        C = K * L * 4
+        self.C = C
+        M = {
+            'point': _Master('point', (K, L, self.rec_stride)),
+            'bn': _Master('bn', (K, L, 8 * Fd)),
+            'c_w0': _Master('c_w0', (C, Fd, G)),
+            'c_bnw': _Master('c_bnw', (C, Fd)),
+            'c_bnb': _Master('c_bnb', (C, Fd)),
+            'c_rm': _Master('c_rm', (C, Fd)),
+            'c_rv': _Master('c_rv', (C, Fd)),
+            'c_w1': _Master('c_w1', (C, Fd, Fd)),
+            'c_b1': _Master('c_b1', (C, Fd)),
+            'nbt': _Master('nbt', (K * L * 8,), torch.int64),
+        }
+        self.masters = M
+        self.grad_masters = ('point', 'c_w0', 'c_bnw', 'c_bnb', 'c_w1', 'c_b1')
+        c = 0
+        n = 0
+        for j in range(K):
+            for l in range(L):
+                ref = self.layers[j][l]
+                m = ref.module
+                off = (j * L + l) * self.rec_stride
+                for X in ('mu', 'logvar'):
+                    t0, t1 = getattr(m, 'T_%s_0' % X), getattr(m, 'T_%s_1' % X)
+                    sd0, bn0, sd1, bn1, sd2 = t0[0], t0[1], t0[3], t0[4], t1[1]
+                    for owner, attr in ((sd0, 'weight'), (bn0, 'weight'), (bn0, 'bias'), (sd1, 'weight'),
+                                        (sd2, 'weight'), (sd2, 'bias')):
+                        t = owner._parameters[attr]
+                        M['point'].add(owner, attr, True, off, t.shape)
+                        off += t.numel()
+                    boff = (j * L + l) * 8 * Fd + (0 if X == 'mu' else 4 * Fd)
+                    for owner, attr in ((bn0, 'running_mean'), (bn0, 'running_var'), (bn1, 'running_mean'),
+                                        (bn1, 'running_var')):
+                        M['bn'].add(owner, attr, False, boff, (Fd,))
+                        boff += Fd
+                    for owner in (bn0, bn1):
+                        M['nbt'].add(owner, 'num_batches_tracked', False, n, ())
+                        n += 1
+                    for which in ('w', 'b'):
+                        seq = getattr(m, 'T_%s_0_cond_%s' % (X, which))
+                        lin0, bn, lin1 = seq[0], seq[1], seq[3]
+                        M['c_w0'].add(lin0, 'weight', True, c * Fd * G, (Fd, G))
+                        M['c_bnw'].add(bn, 'weight', True, c * Fd, (Fd,))
+                        M['c_bnb'].add(bn, 'bias', True, c * Fd, (Fd,))
+                        M['c_rm'].add(bn, 'running_mean', False, c * Fd, (Fd,))
+                        M['c_rv'].add(bn, 'running_var', False, c * Fd, (Fd,))
+                        M['c_w1'].add(lin1, 'weight', True, c * Fd * Fd, (Fd, Fd))
+                        M['c_b1'].add(lin1, 'bias', True, c * Fd, (Fd,))
+                        M['nbt'].add(bn, 'num_batches_tracked', False, n, ())
+                        n += 1
+                        c += 1
+        assert c == C and n == K * L * 8
+
+    def _is_flat(self):
+        for ms in self.masters.values():
+            if ms.tensor is None:
+                return False
+            base = ms.tensor.data_ptr()
+            esz = ms.tensor.element_size()
+            for m in (ms.members[0], ms.members[-1]):
+                if ms.current(m).data_ptr() != base + m[3] * esz:
+                    return False
+        return True
+
+    @torch.no_grad()
+    def flatten(self):
+        """(Re)build the masters from the current module tensors and re-point the modules at them.
+        Needed once, and again after `.to()/.cuda()` (which re-allocates every tensor separately)."""
+        dev = self.layers[0][0].point[0].device
+        for name, ms in self.masters.items():
+            first = ms.current(ms.members[0])
+            if first.dtype != ms.dtype:
+                raise nat.GwtfError('the flow stack holds fp32 parameters (got %s)' % first.dtype)
+            flat = torch.zeros(ms.shape, device=dev, dtype=ms.dtype)
+            fv = flat.view(-1)
+            for m in ms.members:
+                owner, attr, is_param, off, shape = m
+                cur = ms.current(m)
+                numel = cur.numel()
+                view = fv[off:off + numel].view(shape)
+                view.copy_(cur.detach().to(dev))
+                if is_param:
+                    cur.data = view
+                else:
+                    owner._buffers[attr] = view
+            if name in self.grad_masters:
+                ms.params = [ms.current(m) for m in ms.members]
+                flat.requires_grad_(True)
+                flat.register_hook(self._make_reduce_hook())
+                flat.register_post_accumulate_grad_hook(self._make_attach_hook(ms))
+            ms.tensor = flat
+            ms.grad_views = None
+
+    def _make_reduce_hook(self):
+        def hook(grad):
+            if self.sync_gradients and _world() > 1:
+                grad = grad.contiguous()
+                dist.all_reduce(grad)
+                grad = grad / _world()
+            return grad
+        return hook
+
+    def _make_attach_hook(self, ms):
+        def hook(master):
+            self._attach_grads(ms)
+        return hook
+
+    def _attach_grads(self, ms):
+        g = ms.tensor.grad
+        if g is None:
+            return
+        if ms.grad_views is None or ms.grad_ptr != g.data_ptr():
+            gv = g.view(-1)
+            ms.grad_views = [gv[m[3]:m[3] + _numel(m[4])].view(m[4]) for m in ms.members]
+            ms.grad_ptr = g.data_ptr()
+        sentinel = ms.params[0]
+        if sentinel.grad is None or sentinel.grad.data_ptr() != g.data_ptr() + ms.members[0][3] * 4:
+            for prm, v in zip(ms.params, ms.grad_views):
+                prm.grad = v
+
+    def prepare(self):
+        """Called at the top of every pass: keep the flat storage valid and honour
+        `optimizer.zero_grad(set_to_none=True)` (parameters lost their .grad -> clear the masters)."""
+        if not self.flat:
+            return
+        if not self._is_flat():
+            self.flatten()
+        for name in self.grad_masters:
+            ms = self.masters[name]
+            if ms.tensor.grad is not None and ms.current(ms.members[0]).grad is None:
+                ms.tensor.grad = None
+                ms.grad_views = None
 
     def pack_params(self):
+        if self.flat:
+            return self.masters['point'].tensor
         pieces = []
         for j in range(self.K):
             for l in range(self.L):
                 ref = self.layers[j][l]
-                n = 0
-                for t in ref.point:
-                    pieces.append(t.reshape(-1))
-                    n += t.numel()
+                n = sum(t.numel() for t in ref.point)
+                pieces += [t.reshape(-1) for t in ref.point]
                 if n < self.rec_stride:
-                    pieces.append(self._pad(self.rec_stride - n, ref.point[0].device))
+                    pieces.append(ref.point[0].new_zeros(self.rec_stride - n))
         return torch.cat(pieces).view(self.K, self.L, self.rec_stride)
 
-    def unpack_param_grads(self, dparams):
-        """Split a (K,L,rec_stride) gradient into per-parameter tensors (list in pack order)."""
-        out = []
-        flat = dparams.view(-1)
-        off = 0
-        for j in range(self.K):
-            for l in range(self.L):
-                base = off
-                for t in self.layers[j][l].point:
-                    out.append(flat[off:off + t.numel()].view_as(t))
-                    off += t.numel()
-                off = base + self.rec_stride
-        return out
-
-    def point_parameters(self):
-        return [t for j in range(self.K) for l in range(self.L) for t in self.layers[j][l].point]
-
     def pack_bn(self):
+        if self.flat:
+            return self.masters['bn'].tensor
         pieces = []
         for j in range(self.K):
             for l in range(self.L):
@@ -133,50 +295,68 @@ class FlowStack:
                     pieces += [bn0.running_mean, bn0.running_var, bn1.running_mean, bn1.running_var]
         return torch.cat(pieces).view(self.K, self.L, 8 * self.F)
 
+    def _cond_tensors(self):
+        """name -> stacked tensor of the C FiLM nets (masters, or gathered per call)."""
+        if self.flat:
+            return {k: self.masters[k].tensor for k in ('c_w0', 'c_bnw', 'c_bnb', 'c_rm', 'c_rv', 'c_w1', 'c_b1')}
+        conds = [c for j in range(self.K) for l in range(self.L) for c in self.layers[j][l].cond]
+        return {'c_w0': torch.stack([c[0].weight for c in conds]), 'c_bnw': torch.stack([c[1].weight for c in conds]),
+                'c_bnb': torch.stack([c[1].bias for c in conds]),
+                'c_rm': torch.stack([c[1].running_mean for c in conds]),
+                'c_rv': torch.stack([c[1].running_var for c in conds]),
+                'c_w1': torch.stack([c[2].weight for c in conds]), 'c_b1': torch.stack([c[2].bias for c in conds])}
+
     @torch.no_grad()
     def update_point_bn(self, bstat, n_total):
         """nn.BatchNorm1d running-stat update from the batch statistics the kernels used.
         bstat (L,K,2,4,F): mean0 | var0 (biased) | mean1 | var1 (biased)."""
         unbias = float(n_total) / max(float(n_total) - 1.0, 1.0)
-        rms, rvs, means, vars_, nbt = [], [], [], [], []
-        bs = bstat.permute(1, 0, 2, 3, 4)   # (K,L,2,4,F)
-        for j in range(self.K):
-            for l in range(self.L):
-                for net, (bn0, bn1) in enumerate(self.layers[j][l].bn_point):
-                    rms += [bn0.running_mean, bn1.running_mean]
-                    rvs += [bn0.running_var, bn1.running_var]
-                    means += [bs[j, l, net, 0], bs[j, l, net, 2]]
-                    vars_ += [bs[j, l, net, 1], bs[j, l, net, 3]]
-                    nbt += [bn0.num_batches_tracked, bn1.num_batches_tracked]
-        torch._foreach_lerp_(rms, means, BN_MOMENTUM)
-        torch._foreach_lerp_(rvs, torch._foreach_mul(vars_, unbias), BN_MOMENTUM)
-        torch._foreach_add_(nbt, 1)
+        K, L, Fd = self.K, self.L, self.F
+        new = bstat.permute(1, 0, 2, 3, 4).clone()
+        new[:, :, :, 1::2, :] *= unbias          # (no host tensor: an H2D copy here would sync the stream)
+        if not self.flat:
+            rs, ns, nbt = [], [], []
+            for j in range(K):
+                for l in range(L):
+                    for net, (bn0, bn1) in enumerate(self.layers[j][l].bn_point):
+                        rs += [bn0.running_mean, bn0.running_var, bn1.running_mean, bn1.running_var]
+                        ns += list(new[j, l, net].unbind(0))
+                        nbt += [bn0.num_batches_tracked, bn1.num_batches_tracked]
+            torch._foreach_lerp_(rs, ns, BN_MOMENTUM)
+            torch._foreach_add_(nbt, 1)
+            return
+        self.masters['bn'].tensor.view(K, L, 2, 4, Fd).lerp_(new, BN_MOMENTUM)
+        # the first K*L*4 counters of each layer block belong to the point-wise BatchNorms
+        nbt = self.masters['nbt'].tensor.view(K * L, 2, 4)
+        nbt[:, :, :2] += 1
 
     # ------------------------------------------------------------------ FiLM nets
     def film(self, g, training, sync):
         """(B,K,L,2,2,F): [...,0,:] = eps + exp(cond_w(g)), [...,1,:] = cond_b(g)."""
-        K, L, Fd = self.K, self.L, self.F
-        conds = [c for j in range(K) for l in range(L) for c in self.layers[j][l].cond]   # C = K*L*4
-        C = len(conds)
-        W0 = torch.stack([c[0].weight for c in conds]).view(C * Fd, self.G)
-        H = F.linear(g, W0)                                                                 # (B, C*F)
-        bw = torch.cat([c[1].weight for c in conds])
-        bb = torch.cat([c[1].bias for c in conds])
-        rm = torch.cat([c[1].running_mean for c in conds])
-        rv = torch.cat([c[1].running_var for c in conds])
+        K, L, Fd, C = self.K, self.L, self.F, self.C
+        T = self._cond_tensors()
+        H = F.linear(g, T['c_w0'].reshape(C * Fd, self.G))                                  # (B, C*F)
+        bw, bb = T['c_bnw'].reshape(-1), T['c_bnb'].reshape(-1)
+        rm, rv = T['c_rm'].reshape(-1), T['c_rv'].reshape(-1)
         if training:
             Hn, mean, var_unb = _batch_norm_train(H, bw, bb, sync)
             with torch.no_grad():
-                torch._foreach_lerp_([c[1].running_mean for c in conds], list(mean.view(C, Fd).unbind(0)), BN_MOMENTUM)
-                torch._foreach_lerp_([c[1].running_var for c in conds], list(var_unb.view(C, Fd).unbind(0)),
-                                     BN_MOMENTUM)
-                torch._foreach_add_([c[1].num_batches_tracked for c in conds], 1)
+                if self.flat:
+                    rm.lerp_(mean, BN_MOMENTUM)
+                    rv.lerp_(var_unb, BN_MOMENTUM)
+                    self.masters['nbt'].tensor.view(K * L, 2, 4)[:, :, 2:] += 1
+                else:
+                    conds = [c for j in range(K) for l in range(L) for c in self.layers[j][l].cond]
+                    torch._foreach_lerp_([c[1].running_mean for c in conds], list(mean.view(C, Fd).unbind(0)),
+                                         BN_MOMENTUM)
+                    torch._foreach_lerp_([c[1].running_var for c in conds], list(var_unb.view(C, Fd).unbind(0)),
+                                         BN_MOMENTUM)
+                    torch._foreach_add_([c[1].num_batches_tracked for c in conds], 1)
         else:
             Hn = (H - rm) * torch.rsqrt(rv + BN_EPS) * bw + bb
         A = Hn * torch.sigmoid(Hn)
-        W1 = torch.stack([c[2].weight for c in conds])                                      # (C,F,F)
-        b1 = torch.stack([c[2].bias for c in conds])                                        # (C,F)
-        O = torch.baddbmm(b1.unsqueeze(1), A.view(-1, C, Fd).transpose(0, 1), W1.transpose(1, 2))  # (C,B,F)
+        O = torch.baddbmm(T['c_b1'].unsqueeze(1), A.view(-1, C, Fd).transpose(0, 1),
+                          T['c_w1'].transpose(1, 2))                                         # (C,B,F)
         O = O.view(K, L, 2, 2, -1, Fd).permute(4, 0, 1, 2, 3, 5)                            # (B,K,L,net,which,F)
         eps = self.layers[0][0].module.eps
         s = eps + torch.exp(O[..., 0, :])
@@ -185,11 +365,11 @@ class FlowStack:
     # ------------------------------------------------------------------ kernels
     def nll_pass(self, p, g, training):
         """-> z (K,B,3,N) base-space samples, ssum (K,B,3,N) per-dim sums of logvar."""
+        self.prepare()
         sync = training and _world() > 1
         film = self.film(g, training, sync)
-        params = self.pack_params()
-        bnbuf = self.pack_bn()
-        z, ssum, bstat, n_total = _StackNLLPass.apply(p.contiguous(), params, film, bnbuf, self, training, sync)
+        z, ssum, bstat, n_total = _StackNLLPass.apply(p.contiguous(), self.pack_params(), film, self.pack_bn(), self,
+                                                      training, sync)
         if training:
             self.update_point_bn(bstat, n_total)
         return z, ssum
@@ -197,6 +377,7 @@ class FlowStack:
     @torch.no_grad()
     def nll_eval_fused(self, p, g, base, logw, want_logp=False):
         """Fused no-grad eval forward -> nll (B,N) [, logp (B,N,K)]."""
+        self.prepare()
         film = self.film(g, False, False)
         params = self.pack_params()
         bnbuf = self.pack_bn()
@@ -209,6 +390,13 @@ class FlowStack:
                                               B, N, nat.ptr(nll), nat.ptr(logp), None, None, _stream_ptr()),
                   'gwtf_nll_fwd_eval')
         return (nll, logp) if want_logp else nll
+
+
+def _numel(shape):
+    n = 1
+    for d in shape:
+        n *= d
+    return n
 
 
 def _batch_norm_train(H, weight, bias, sync):
@@ -298,7 +486,10 @@ class _StackNLLPass(torch.autograd.Function):
         ctx.training = training
         ctx.sync = sync
         ctx.n_total = n_total
-        ctx.save_for_backward(p, params, film, bnbuf, ubuf, mom, sum1)
+        # running stats are updated in place right after a train-mode forward (and are not read by
+        # the train-mode backward), so they must not go through save_for_backward's version check
+        ctx.bnbuf = bnbuf
+        ctx.save_for_backward(p, params, film, ubuf, mom, sum1)
         z = ubuf[0]
         ctx.mark_non_differentiable(*([bstat] if bstat is not None else []))
         return z, ssum, bstat, n_total
@@ -307,7 +498,8 @@ class _StackNLLPass(torch.autograd.Function):
     def backward(ctx, dz, dssum, _dbstat, _dn):
         lib = nat.lib()
         stack = ctx.stack
-        p, params, film, bnbuf, ubuf, mom, sum1 = ctx.saved_tensors
+        p, params, film, ubuf, mom, sum1 = ctx.saved_tensors
+        bnbuf = ctx.bnbuf
         K, L, Fd = stack.K, stack.L, stack.F
         B, _, N = p.shape
         dev = p.device
@@ -421,6 +613,7 @@ def sample_mixture(stack, g, mu_base, lv_base, logits, n_points, seed, stream_id
         raise nat.GwtfError('the flow stack runs on CUDA tensors only (got %s)' % g.device)
     B = g.shape[0]
     dev = g.device
+    stack.prepare()
     film = stack.film(g, False, False)
     params = stack.pack_params()
     bnbuf = stack.pack_bn()
@@ -462,6 +655,7 @@ def run_module_stack(stack, p, g, mode, training):
     B, _, N = p.shape
     dev = p.device
     sync = training and _world() > 1
+    stack.prepare()
     film = stack.film(g, training, sync)
     params = stack.pack_params()
     bnbuf = stack.pack_bn()

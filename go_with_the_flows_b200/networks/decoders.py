@@ -60,5 +60,5 @@ class LocalCondRNVPDecoder(nn.Module):
         direct -> ps[-1] is the data-space sample; inverse -> ps[0] is the base-space sample
         (decoders.py:65-77)."""
         if self._stack is None:
-            self._stack = FlowStack([self.coupling_layers()])
+            self._stack = FlowStack([self.coupling_layers()], own_storage=False)
         return run_module_stack(self._stack, p, g, mode, self.training)

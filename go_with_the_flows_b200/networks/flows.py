@@ -75,7 +75,7 @@ class CondRealNVPFlow3D(nn.Module):
 
     def forward(self, p, g, mode='direct'):
         if self._stack is None:
-            self._stack = FlowStack([[self]])
+            self._stack = FlowStack([[self]], own_storage=False)
         ps, mus, lvs = run_module_stack(self._stack, p, g, mode, self.training)
         return ps[0], mus[0], lvs[0]
 
@@ -105,7 +105,7 @@ class CondRealNVPFlow3DTriple(nn.Module):
 
     def forward(self, p, g, mode='direct'):
         if self._stack is None:
-            self._stack = FlowStack([self.coupling_layers()])
+            self._stack = FlowStack([self.coupling_layers()], own_storage=False)
         # both modes return [p1, p2, p3] indexed by layer (flows.py:160)
         return run_module_stack(self._stack, p, g, mode, self.training)
 
