@@ -168,3 +168,18 @@ def test_native_library_is_the_code_that_ran():
     _native.lib()
     maps = open('/proc/self/maps').read()
     assert os.path.basename(_native.LIB_PATH) in maps
+
+
+def test_two_gpu_syncbn_equals_concatenated_batch():
+    """Needs 2 GPUs (gpurun --gpus 2); skipped on a single-GPU box."""
+    import os
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 GPUs')
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node=2',
+                          '--master-addr', '127.0.0.1', '--master-port', '29533',
+                          os.path.join(root, 'tests', 'dist_gpu_parity.py')], capture_output=True, text=True,
+                         timeout=600)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
