@@ -23,6 +23,7 @@ _D = ctypes.POINTER(StackDesc)
 # name -> argtypes; every function returns int (0 = ok)
 _SIGNATURES = {
     'gwtf_version': [],
+    'gwtf_set_tensor_cores': [c_i],
     'gwtf_rec_stride': [c_i],
     'gwtf_param_offsets': [c_i, c_i, ctypes.POINTER(c_i), ctypes.POINTER(c_i)],
     'gwtf_fma_peak_tflops': [c_i, ctypes.POINTER(c_d), c_f],

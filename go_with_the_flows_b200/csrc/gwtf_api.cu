@@ -1,11 +1,13 @@
 // C ABI of libgwtf.so (see include/gwtf.h).  Host-side argument checks, template dispatch on
 // the padded feature width, launches on the caller's stream.  No allocation, no host sync.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <cuda_runtime.h>
 
 #include "gwtf_common.cuh"
 #include "gwtf_fwd.cuh"
+#include "gwtf_tc_fwd.cuh"
 #include "gwtf_bwd.cuh"
 #include "gwtf_sample.cuh"
 
@@ -42,6 +44,16 @@ int check_desc(const gwtf_stack_desc* d) {
     return 0;
 }
 
+int g_use_tc = -1;    // -1: decide from the environment (GWTF_TC, default on), 0 / 1: forced
+
+bool use_tc(int F) {
+    if (g_use_tc < 0) {
+        const char* e = getenv("GWTF_TC");
+        g_use_tc = (e && e[0] == '0') ? 0 : 1;
+    }
+    return g_use_tc == 1 && F <= 39;    // tensor-memory tile budget: F + 1 (bias channel) <= 40; configs use 33 / 37
+}
+
 int padded_features(int F) {
     const int opts[] = {8, 16, 24, 32, 36, 40, 48, 64};
     for (int o : opts) if (F <= o) return o;
@@ -67,6 +79,9 @@ int blocks_per_sm(KernelT kernel, size_t smem) {
 
 template <typename KernelT>
 cudaError_t allow_smem(KernelT kernel, size_t smem) {
+    // ask for the full shared-memory carveout: the default preference sizes L1 vs shared from a
+    // heuristic and the occupancy query then reports 1 CTA/SM for 60-80 KB blocks
+    cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 }
 
@@ -100,6 +115,50 @@ int launch_eval(const EvalArgs& a0, cudaStream_t st) {
     return 0;
 }
 
+#define GWTF_DISPATCH_TC(F, CALL)                                         \
+    switch ((F + 8) / 8) {                                                \
+        case 1: { constexpr int FPK = 8,  FPN = 16; CALL; } break;        \
+        case 2: { constexpr int FPK = 16, FPN = 16; CALL; } break;        \
+        case 3: { constexpr int FPK = 24, FPN = 32; CALL; } break;        \
+        case 4: { constexpr int FPK = 32, FPN = 32; CALL; } break;        \
+        case 5: { constexpr int FPK = 40, FPN = 48; CALL; } break;        \
+        default: return fail(-4, "unsupported feature width for the tensor-core path"); \
+    }
+
+template <typename KernelT>
+int blocks_per_sm_n(KernelT kernel, int threads, size_t smem) {
+    int n = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, threads, smem);
+    return n < 1 ? 1 : n;
+}
+
+template <int FPK, int FPN, int PHASE>
+int launch_fwd_layer_tc(const LayerArgs& a0, cudaStream_t st) {
+    LayerArgs a = a0;
+    a.tiles_per_shape = (a.N + kTcThreads - 1) / kTcThreads;
+    const int F = a.d.n_features;
+    const size_t smem = round_up((int)sizeof(TcFwdSmem<FPK, FPN>), 16) + (size_t)round_up(raw_floats(F), 4) * 4;
+    auto kern = k_fwd_layer_tc<FPK, FPN, PHASE>;
+    GWTF_CUDA(allow_smem(kern, smem));
+    const int tiles = a.B * a.tiles_per_shape;
+    const int K = a.d.n_components;
+    // the occupancy API reports 1 CTA/SM for tcgen05 kernels; size the grid from the real limits
+    // (shared memory, tensor-memory columns) -- the hardware co-schedules what fits
+    int per_sm = (int)((227 * 1024) / (smem + 1024));
+    (void)blocks_per_sm_n(kern, kTcThreads, smem);
+    if (getenv("GWTF_DEBUG")) {
+        static int once = 0;
+        if (!once++) fprintf(stderr, "[gwtf] tc fwd: occupancy %d CTAs/SM, smem %zu, sms %d, err=%s\n", per_sm, smem, num_sms(), cudaGetErrorString(cudaPeekAtLastError()));
+    }
+    if (per_sm > 512 / kTcCols) per_sm = 512 / kTcCols;          // tensor-memory columns per SM
+    int gx = (num_sms() * per_sm + K - 1) / K;
+    if (gx > tiles) gx = tiles;
+    if (gx < 1) gx = 1;
+    kern<<<dim3(gx, K), kTcThreads, smem, st>>>(a);
+    GWTF_CUDA(cudaGetLastError());
+    return 0;
+}
+
 template <int FP, int PHASE>
 int launch_fwd_layer(const LayerArgs& a0, cudaStream_t st) {
     constexpr int P = PointsPerThread<FP>::fwd;
@@ -124,6 +183,12 @@ int launch_fwd_layer(const LayerArgs& a0, cudaStream_t st) {
 extern "C" {
 
 int gwtf_version(void) { return 1; }
+
+int gwtf_set_tensor_cores(int32_t enable) {
+    const int prev = g_use_tc;
+    g_use_tc = enable < 0 ? -1 : (enable ? 1 : 0);
+    return prev;
+}
 const char* gwtf_last_error_string(void) { return g_err; }
 
 int gwtf_rec_stride(int32_t F) { return rec_stride_of(F); }
@@ -180,6 +245,11 @@ int gwtf_fwd_layer_ex(const gwtf_stack_desc* desc, int32_t layer, int32_t phase,
     a.d = *desc; a.layer = layer; a.train = train; a.direct = direct; a.params = params; a.bnbuf = bnbuf; a.film = film;
     a.xin = xin; a.xin_shared = xin_shared; a.xout = xout; a.ld = ld; a.ssum = ssum; a.trio = trio;
     a.mom_in = mom_in; a.mom_out = mom_out; a.sum1 = sum1; a.B = B; a.N = N; a.n_total = n_total; a.tiles_per_shape = 0;
+    if (use_tc(desc->n_features)) {
+        if (phase == 0) { GWTF_DISPATCH_TC(desc->n_features, return (launch_fwd_layer_tc<FPK, FPN, 0>(a, (cudaStream_t)stream))); }
+        else { GWTF_DISPATCH_TC(desc->n_features, return (launch_fwd_layer_tc<FPK, FPN, 1>(a, (cudaStream_t)stream))); }
+        return 0;
+    }
     if (phase == 0) { GWTF_DISPATCH_FP(desc->n_features, return (launch_fwd_layer<FP, 0>(a, (cudaStream_t)stream))); }
     else { GWTF_DISPATCH_FP(desc->n_features, return (launch_fwd_layer<FP, 1>(a, (cudaStream_t)stream))); }
     return 0;

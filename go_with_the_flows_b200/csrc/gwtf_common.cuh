@@ -126,14 +126,12 @@ __device__ __forceinline__ void bn0_from_moments(const double* mom, double n, co
     var0 = (float)fmax(v, 0.0);
 }
 
-// Build the compute layout from the raw record.  All threads of the CTA participate; caller
-// syncs before (raw complete) and after (W ready).
-//   train: BN statistics come from mom / sum1 (batch stats), else from the raw bn block.
-//   phase0: only q0 + W1T are needed (statistics pass).
-template <int FP, bool BWD>
-__device__ __forceinline__ void stage_layer(LayerW<FP>& W, LayerWB<FP>* WB, const float* raw, const LayerSrc& src,
-                                            int F, unsigned wmask, bool train, bool phase0, const double* bsum1,
-                                            int tid, int nthreads) {
+// Per-channel vectors (q0, r0, mi1, w2, b2, ...) of one layer for any struct with those members and
+// FPV entries per net.
+template <int FPV, bool BWD, class WT, class WBT>
+__device__ __forceinline__ void stage_vectors(WT& W, WBT* WB, const float* raw, const LayerSrc& src, int F,
+                                              unsigned wmask, bool train, bool phase0, const double* bsum1, int tid,
+                                              int nthreads) {
     const int w = popc3(wmask), k = 3 - w;
     const NetOffsets o = net_offsets(F, w);
     int keepd[3], warpd[3];
@@ -145,9 +143,8 @@ __device__ __forceinline__ void stage_layer(LayerW<FP>& W, LayerWB<FP>* WB, cons
     }
     const int rs = rec_stride_of(F);
     const float* bn = raw + rs;
-    // --- per-channel pieces: 2 nets x FP channels
-    for (int i = tid; i < 2 * FP; i += nthreads) {
-        const int net = i / FP, c = i - net * FP;
+    for (int i = tid; i < 2 * FPV; i += nthreads) {
+        const int net = i / FPV, c = i - net * FPV;
         float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
         float4 r = q;
         float4 w2 = q;
@@ -199,6 +196,18 @@ __device__ __forceinline__ void stage_layer(LayerW<FP>& W, LayerWB<FP>* WB, cons
         if (!phase0) for (int a = 0; a < w; ++a) ba[warpd[a]] = P[o.b2 + a];
         W.b2[tid] = make_float4(ba[0], ba[1], ba[2], 0.f);
     }
+}
+
+// Build the compute layout from the raw record.  All threads of the CTA participate; caller
+// syncs before (raw complete) and after (W ready).
+//   train: BN statistics come from mom / sum1 (batch stats), else from the raw bn block.
+//   phase0: only q0 + W1T are needed (statistics pass).
+template <int FP, bool BWD>
+__device__ __forceinline__ void stage_layer(LayerW<FP>& W, LayerWB<FP>* WB, const float* raw, const LayerSrc& src,
+                                            int F, unsigned wmask, bool train, bool phase0, const double* bsum1,
+                                            int tid, int nthreads) {
+    stage_vectors<FP, BWD>(W, WB, raw, src, F, wmask, train, phase0, bsum1, tid, nthreads);
+    const NetOffsets o = net_offsets(F, popc3(wmask));
     // --- sd1 weight, transposed + zero padded
     for (int i = tid; i < 2 * FP * FP; i += nthreads) {
         const int net = i / (FP * FP), rem = i - net * FP * FP;
@@ -211,9 +220,8 @@ __device__ __forceinline__ void stage_layer(LayerW<FP>& W, LayerWB<FP>* WB, cons
 
 // FiLM fold for one shape: st = (s*istd1, t - s*mean1*istd1).  `film` = 4F floats (smem or global):
 // s_mu | t_mu | s_lv | t_lv.  Needs W.mi1 (stage_layer) to be visible.
-template <int FP, bool BWD>
-__device__ __forceinline__ void stage_film(LayerW<FP>& W, LayerWB<FP>* WB, const float* film, int F, int tid,
-                                           int nthreads) {
+template <int FP, bool BWD, class WT, class WBT>
+__device__ __forceinline__ void stage_film(WT& W, WBT* WB, const float* film, int F, int tid, int nthreads) {
     for (int i = tid; i < 2 * FP; i += nthreads) {
         const int net = i / FP, c = i - net * FP;
         float2 st = make_float2(0.f, 0.f);

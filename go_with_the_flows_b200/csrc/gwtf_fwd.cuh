@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(kThreads) k_nll_eval(const EvalArgs a) {
         stage_layer<FP, false>(S.W, nullptr, rawb[buf], LayerSrc(), F, a.d.warp_mask[l], false, false, nullptr, tid,
                                kThreads);
         __syncthreads();
-        stage_film<FP, false>(S.W, nullptr, rawb[buf] + rec_stride_of(F) + 8 * F, F, tid, kThreads);
+        stage_film<FP, false>(S.W, (LayerWB<FP>*)nullptr, rawb[buf] + rec_stride_of(F) + 8 * F, F, tid, kThreads);
         __syncthreads();
         if (tid == 0 && s + 1 < total) issue_layer_copy(rawb[buf ^ 1], src_of(s + 1), F, true, true, &S.bar[buf ^ 1]);
 
@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(kThreads) k_fwd_layer(const LayerArgs a) {
         const int n0 = (t - b * a.tiles_per_shape) * (kThreads * P);
         if (PHASE == 1 && b != cur_b) {
             __syncthreads();
-            stage_film<FP, false>(S.W, nullptr, a.film + ((size_t)(b * K + j) * L + l) * 4 * F, F, tid, kThreads);
+            stage_film<FP, false>(S.W, (LayerWB<FP>*)nullptr, a.film + ((size_t)(b * K + j) * L + l) * 4 * F, F, tid, kThreads);
             __syncthreads();
             cur_b = b;
         }

@@ -91,7 +91,7 @@ __device__ __forceinline__ void sample_chunk(const SampleArgs& a, SampleSmem<FP>
         stage_layer<FP, false>(S.W, nullptr, rawb[buf], LayerSrc(), F, a.d.warp_mask[l], false, false, nullptr, tid,
                                kThreads);
         __syncthreads();
-        stage_film<FP, false>(S.W, nullptr, rawb[buf] + rec_stride_of(F) + 8 * F, F, tid, kThreads);
+        stage_film<FP, false>(S.W, (LayerWB<FP>*)nullptr, rawb[buf] + rec_stride_of(F) + 8 * F, F, tid, kThreads);
         __syncthreads();
         {   // prefetch the next record of the stream
             int nj = j, ncb = cb, nl = l + 1;

@@ -54,6 +54,10 @@ typedef struct gwtf_stack_desc {
 } gwtf_stack_desc;
 
 int gwtf_version(void);
+/* Contraction engine of the per-layer kernels: 1 = tcgen05 tensor cores (3xTF32, TMEM accumulators;
+ * default, feature widths <= 40), 0 = FP32 FMA pipe, -1 = re-read the GWTF_TC environment variable.
+ * Returns the previous setting (NOT an error code). */
+int gwtf_set_tensor_cores(int32_t enable);
 const char* gwtf_last_error_string(void);
 
 /* Record geometry shared with the Python packer.  offsets[0..5] = W0,bn0.weight,bn0.bias,W1,W2,b2

@@ -3,7 +3,7 @@ import numpy as np
 import torch
 
 from oracle import flow_oracle as fo
-from tests.util import Golden, build_dropin, max_rel, rel_l2
+from tests.util import Golden, build_dropin, max_rel, nll_err, rel_l2
 
 DECODER_PREFIXES = ('pc_decoder', 'p_prior', 'mixture_weights')
 
@@ -20,7 +20,7 @@ def oracle_fp32_errors(gd, tag):
     out = fo.mixture_nll(p, g, sd, base_type=gd.meta['p_decoder_base_type'], weights_type=gd.meta['weights_type'],
                          training=training, base_var=gd.meta['p_decoder_base_var'])
     out['pnll'].backward()
-    errs = {'nll': max_rel(out['nll'].detach(), gd.t(f'{tag}/nll')),
+    errs = {'nll': nll_err(out['nll'].detach(), gd.t(f'{tag}/nll')),
             'dp': rel_l2(p.grad, gd.t(f'{tag}/dp')), 'dg': rel_l2(g.grad, gd.t(f'{tag}/dg'))}
     num = den = 0.0
     for k in gd.keys(f'{tag}/grad/'):
@@ -49,7 +49,7 @@ def dropin_nll_errors(gd, tag, fused_nll=True, device='cuda'):
     pnll.backward()
     res = {}
     if fused_nll:
-        res['nll'] = max_rel(out_dec[0]['mixture_nll'].detach().cpu(), gd.t(f'{tag}/nll'))
+        res['nll'] = nll_err(out_dec[0]['mixture_nll'].detach().cpu(), gd.t(f'{tag}/nll'))
     else:
         z = torch.stack([od['p_prior_samples'][0] for od in out_dec], 1)
         res['z'] = max_rel(z.detach().cpu(), gd.t(f'{tag}/z'), floor=1e-3)
@@ -99,7 +99,7 @@ def dropin_eval_fused_error(gd, device='cuda'):
     with torch.no_grad():
         out_dec, logits = model.decode(p, g, p.shape[2])
     nll = out_dec[0]['mixture_nll']
-    return max_rel(nll.cpu(), gd.t('eval/nll'))
+    return nll_err(nll.cpu(), gd.t('eval/nll'))
 
 
 def dropin_sample_errors(gd, device='cuda'):

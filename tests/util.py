@@ -68,3 +68,11 @@ def build_dropin(gd, device='cpu'):
     model = Flow_Mixture_Model(**golden_cfg(gd))
     model.load_state_dict(gd.sd(torch.float32), strict=True)
     return model.to(device)
+
+
+def nll_err(a, b):
+    """Per-point log-likelihood error with a mixed tolerance: |a-b| / max(|b|, 1).  A pure relative
+    error is ill-defined where a point's NLL crosses zero (the 'fixed'-base golden case)."""
+    a = a.double()
+    b = b.double()
+    return float(((a - b).abs() / b.abs().clamp_min(1.0)).max())

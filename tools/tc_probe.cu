@@ -144,6 +144,80 @@ __global__ void __launch_bounds__(128) k_g3(const float* A, const float* B, floa
     if (warp == 0) tmem_dealloc(tbase, 128);
 }
 
+// ---------------------------------------------------------------------------------------------
+// cycle breakdown of one "contraction call" (P tiles): st | sync | mma+commit+wait | ld
+__global__ void __launch_bounds__(128) k_time(const float* A, const float* B, float* D, long long* cyc, int iters, int P) {
+    __shared__ __align__(128) float sB[2][NP * KP];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    if (warp == 0) tmem_alloc(&tmem_base_s, 256);
+    if (tid == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
+    for (int i = tid; i < NP * KP; i += 128) {
+        const int n = i / KP, k = i - n * KP;
+        float hi, lo;
+        split_tf32(B[i], hi, lo);
+        const int off = kmajor_offset(n, k, KP);
+        sB[0][off] = hi; sB[1][off] = lo;
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tbase = tmem_base_s;
+    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    float hi[KP], lo[KP];
+#pragma unroll
+    for (int k = 0; k < KP; ++k) split_tf32(A[tid * KP + k], hi[k], lo[k]);
+    long long t_st = 0, t_sync = 0, t_mma = 0, t_ld = 0;
+    uint32_t phase = 0;
+    float sink = 0.f;
+    for (int it = 0; it < iters; ++it) {
+        long long c0 = clock64();
+        for (int p = 0; p < P; ++p) {
+            tmem_st<KP>(tbase + lane_base + p * 128 + 48, hi);
+            tmem_st<KP>(tbase + lane_base + p * 128 + 88, lo);
+        }
+        tmem_wait_st();
+        long long c1 = clock64();
+        tc_fence_before();
+        __syncthreads();
+        long long c2 = clock64();
+        if (tid == 0) {
+            tc_fence_after();
+            const uint32_t idesc = make_idesc_tf32(128, NP, 0, 0);
+            const uint64_t bhi = make_smem_desc_kmajor(sB[0], KP), blo = make_smem_desc_kmajor(sB[1], KP);
+            for (int p = 0; p < P; ++p) {
+                bool acc = false;
+                for (int pass = 0; pass < 3; ++pass) {
+                    const uint32_t a = tbase + p * 128 + (pass == 1 ? 88 : 48);
+                    const uint64_t b = pass == 2 ? blo : bhi;
+                    for (int s = 0; s < KP / 8; ++s) { mma_tf32_ts(tbase + p * 128, a + 8 * s, b + (uint64_t)(16 * s), idesc, acc); acc = true; }
+                }
+            }
+            tc_commit(&bar);
+        }
+        mbar_wait(&bar, phase);
+        phase ^= 1u;
+        tc_fence_after();
+        long long c3 = clock64();
+        for (int p = 0; p < P; ++p) {
+            float d[NP];
+            tmem_ld<NP>(tbase + lane_base + p * 128, d);
+            tmem_wait_ld();
+#pragma unroll
+            for (int n = 0; n < NP; ++n) sink += d[n];
+        }
+        long long c4 = clock64();
+        t_st += c1 - c0; t_sync += c2 - c1; t_mma += c3 - c2; t_ld += c4 - c3;
+    }
+    if (tid == 0 && blockIdx.x == 0) { cyc[0] = t_st; cyc[1] = t_sync; cyc[2] = t_mma; cyc[3] = t_ld; }
+    D[blockIdx.x * 128 + tid] = sink;
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tbase, 256);
+}
+
 static double frand() { return (double)rand() / RAND_MAX * 2.0 - 1.0; }
 
 int main() {
@@ -197,6 +271,28 @@ int main() {
         printf("G3 variant %d (SS, MN-major A and B, 3xTF32): max abs err %.3e  (max |ref| %.3f)  %s\n", variant, maxerr, maxref,
                maxerr < 5e-5 ? "OK" : "FAIL");
         printf("   D[0][0..3] = %g %g %g %g   D[5][7]=%g\n", D[0], D[1], D[2], D[3], D[5 * N3 + 7]);
+        }
+    }
+    {   // ---- timing
+        std::vector<float> A(128 * KP), B(NP * KP);
+        for (auto& v : A) v = (float)frand();
+        for (auto& v : B) v = (float)frand();
+        float *dA, *dB, *dD; long long* dC;
+        CK(cudaMalloc(&dA, A.size() * 4)); CK(cudaMalloc(&dB, B.size() * 4)); CK(cudaMalloc(&dD, 148 * 4 * 128 * 4)); CK(cudaMalloc(&dC, 64));
+        CK(cudaMemcpy(dA, A.data(), A.size() * 4, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(dB, B.data(), B.size() * 4, cudaMemcpyHostToDevice));
+        for (int grid : {1, 148, 296}) for (int P : {1, 2}) {
+            const int iters = 200;
+            cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+            k_time<<<grid, 128>>>(dA, dB, dD, dC, iters, P);
+            cudaEventRecord(e0);
+            k_time<<<grid, 128>>>(dA, dB, dD, dC, iters, P);
+            cudaEventRecord(e1);
+            CK(cudaDeviceSynchronize());
+            float ms; cudaEventElapsedTime(&ms, e0, e1);
+            long long c[4]; CK(cudaMemcpy(c, dC, 32, cudaMemcpyDeviceToHost));
+            printf("time grid %3d P %d: %.3f ms total, per call: st %lld sync %lld mma+wait %lld ld %lld cycles (%.2f us/call)\n", grid, P, ms,
+                   c[0] / iters, c[1] / iters, c[2] / iters, c[3] / iters, ms * 1e3 / iters);
         }
     }
     return 0;
