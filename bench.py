@@ -184,6 +184,7 @@ def kernel_only_times(model, p, g, reps):
         logits = model.get_weights(g)
         logw = (logits - torch.logsumexp(logits, -1, keepdim=True)).contiguous()
     ubuf = torch.empty(L, K, B, 3, N, device=dev)
+    ybuf = None      # recompute h1 in backward (keeping y1 measured slower; FlowStack.keep_activations)
     ld = torch.zeros(K, B, N, device=dev)
     mom = torch.zeros(L, K, nat.MOM_STRIDE, device=dev, dtype=torch.float64)
     sum1 = torch.zeros(L, K, 2, 2, Fd, device=dev, dtype=torch.float64)
@@ -205,11 +206,11 @@ def kernel_only_times(model, p, g, reps):
 
     def fwd():
         nat.check(lib.gwtf_fwd_all(desc, 1, P(params), P(bnbuf), P(film), P(p), P(base), P(logw), P(ubuf), P(ld), None,
-                                   P(mom), P(sum1), P(bstat), B, N, P(nll), None, _stream_ptr()), 'gwtf_fwd_all')
+                                   P(ybuf), P(mom), P(sum1), P(bstat), B, N, P(nll), None, _stream_ptr()), 'gwtf_fwd_all')
 
     def bwd():
         bsum.zero_()
-        nat.check(lib.gwtf_bwd_all(desc, 1, P(params), P(bnbuf), P(film), P(p), P(base), P(logw), P(ubuf), P(ld),
+        nat.check(lib.gwtf_bwd_all(desc, 1, P(params), P(bnbuf), P(film), P(p), P(base), P(logw), P(ubuf), P(ybuf), P(ld),
                                    P(mom), P(sum1), P(nll), P(dnll), P(bsum), P(gbuf), P(gs), P(dobuf), P(dparams),
                                    P(dfilm), P(dbase), P(dlogw), P(dpoints), B, N, _stream_ptr()), 'gwtf_bwd_all')
 
@@ -218,9 +219,9 @@ def kernel_only_times(model, p, g, reps):
         for l in (range(L - 1, -1, -1) if kind == 'fwd' else range(L)):
             if kind == 'fwd':
                 nat.check(lib.gwtf_fwd_layer(desc, l, phase, 1, P(params), P(bnbuf), P(film), P(p), P(ubuf), P(ld),
-                                             None, P(mom), P(sum1), B, N, n_total, st), 'gwtf_fwd_layer')
+                                             None, P(ybuf), P(mom), P(sum1), B, N, n_total, st), 'gwtf_fwd_layer')
             else:
-                nat.check(lib.gwtf_bwd_layer(desc, l, phase, 1, P(params), P(bnbuf), P(film), P(p), P(ubuf), P(mom),
+                nat.check(lib.gwtf_bwd_layer(desc, l, phase, 1, P(params), P(bnbuf), P(film), P(p), P(ubuf), P(ybuf), P(mom),
                                              P(sum1), P(bsum), P(gbuf), P(gs), P(dobuf), P(dparams), P(dfilm), B, N,
                                              n_total, st), 'gwtf_bwd_layer')
 

@@ -29,17 +29,15 @@ _SIGNATURES = {
     'gwtf_fma_peak_tflops': [c_i, ctypes.POINTER(c_d), c_f],
     'gwtf_nll_fwd_eval': [_D, c_f, c_f, c_f, c_f, c_f, c_f, c_i, c_i, c_f, c_f, c_f, c_f, c_f],
     'gwtf_fwd_moments': [_D, c_f, c_i, c_i, c_f, c_f],
-    'gwtf_fwd_layer': [_D, c_i, c_i, c_i, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_i, c_i, c_d, c_f],
-    'gwtf_fwd_layer_ex': [_D, c_i, c_i, c_i, c_i, c_f, c_f, c_f, c_f, c_i, c_f, c_f, c_f, c_f, c_f, c_f, c_f,
-                          c_i, c_i, c_d, c_f],
+    'gwtf_fwd_layer': [_D, c_i, c_i, c_i] + [c_f] * 10 + [c_i, c_i, c_d, c_f],
+    'gwtf_fwd_layer_ex': [_D, c_i, c_i, c_i, c_i, c_f, c_f, c_f, c_f, c_i] + [c_f] * 8 + [c_i, c_i, c_d, c_f],
     'gwtf_fwd_bstat': [_D, c_f, c_f, c_f, c_d, c_f, c_f],
     'gwtf_nll_from_state': [_D, c_f, c_f, c_f, c_f, c_i, c_i, c_f, c_f, c_f],
-    'gwtf_fwd_all': [_D, c_i, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_i, c_i, c_f, c_f, c_f],
+    'gwtf_fwd_all': [_D, c_i] + [c_f] * 13 + [c_i, c_i, c_f, c_f, c_f],
     'gwtf_bwd_seed': [_D, c_f, c_f, c_f, c_f, c_f, c_f, c_i, c_i, c_f, c_f, c_f, c_f, c_f],
-    'gwtf_bwd_layer': [_D, c_i, c_i, c_i, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f,
-                       c_i, c_i, c_d, c_f],
+    'gwtf_bwd_layer': [_D, c_i, c_i, c_i] + [c_f] * 14 + [c_i, c_i, c_d, c_f],
     'gwtf_bwd_finish': [_D, c_i, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_i, c_i, c_d, c_f],
-    'gwtf_bwd_all': [_D, c_i] + [c_f] * 21 + [c_i, c_i, c_f],
+    'gwtf_bwd_all': [_D, c_i] + [c_f] * 22 + [c_i, c_i, c_f],
     'gwtf_sample': [_D, c_f, c_f, c_f, c_f, c_f, c_i, c_i, ctypes.c_uint64, ctypes.c_uint32, c_f, c_f,
                     c_f, c_f, c_f, c_f],
 }

@@ -231,8 +231,9 @@ int gwtf_fwd_moments(const gwtf_stack_desc* desc, const float* points, int32_t B
 // mom / sum1 between phases; xin_shared=1 when `xin` is the (B,3,N) data cloud.
 int gwtf_fwd_layer_ex(const gwtf_stack_desc* desc, int32_t layer, int32_t phase, int32_t train, int32_t direct,
                       const float* params, const float* bnbuf, const float* film, const float* xin,
-                      int32_t xin_shared, float* xout, float* ld, float* ssum, float* trio, const double* mom_in,
-                      double* mom_out, double* sum1, int32_t B, int32_t N, double n_total, void* stream) {
+                      int32_t xin_shared, float* xout, float* ld, float* ssum, float* trio, float* y1out,
+                      const double* mom_in, double* mom_out, double* sum1, int32_t B, int32_t N, double n_total,
+                      void* stream) {
     if (int rc = check_desc(desc)) return rc;
     if (layer < 0 || layer >= desc->n_layers) return fail(-12, "layer out of range");
     if (phase != 0 && phase != 1) return fail(-13, "phase must be 0 or 1");
@@ -243,7 +244,7 @@ int gwtf_fwd_layer_ex(const gwtf_stack_desc* desc, int32_t layer, int32_t phase,
     if (B <= 0 || N <= 0) return 0;
     LayerArgs a;
     a.d = *desc; a.layer = layer; a.train = train; a.direct = direct; a.params = params; a.bnbuf = bnbuf; a.film = film;
-    a.xin = xin; a.xin_shared = xin_shared; a.xout = xout; a.ld = ld; a.ssum = ssum; a.trio = trio;
+    a.xin = xin; a.xin_shared = xin_shared; a.xout = xout; a.ld = ld; a.ssum = ssum; a.trio = trio; a.y1out = y1out;
     a.mom_in = mom_in; a.mom_out = mom_out; a.sum1 = sum1; a.B = B; a.N = N; a.n_total = n_total; a.tiles_per_shape = 0;
     if (use_tc(desc->n_features)) {
         if (phase == 0) { GWTF_DISPATCH_TC(desc->n_features, return (launch_fwd_layer_tc<FPK, FPN, 0>(a, (cudaStream_t)stream))); }
@@ -257,7 +258,7 @@ int gwtf_fwd_layer_ex(const gwtf_stack_desc* desc, int32_t layer, int32_t phase,
 
 int gwtf_fwd_layer(const gwtf_stack_desc* desc, int32_t layer, int32_t phase, int32_t train, const float* params,
                    const float* bnbuf, const float* film, const float* points, float* ubuf, float* ld, float* ssum,
-                   double* mom, double* sum1, int32_t B, int32_t N, double n_total, void* stream) {
+                   float* ybuf, double* mom, double* sum1, int32_t B, int32_t N, double n_total, void* stream) {
     if (int rc = check_desc(desc)) return rc;
     if (!ubuf) return fail(-10, "null pointer argument");
     const int L = desc->n_layers, K = desc->n_components, F = desc->n_features;
@@ -268,9 +269,10 @@ int gwtf_fwd_layer(const gwtf_stack_desc* desc, int32_t layer, int32_t phase, in
     double* mom_in = mom ? mom + (size_t)layer * K * GWTF_MOM_STRIDE : nullptr;
     double* mom_out = (mom && layer > 0) ? mom + (size_t)(layer - 1) * K * GWTF_MOM_STRIDE : nullptr;
     double* s1 = sum1 ? sum1 + (size_t)layer * K * 4 * F : nullptr;
+    float* y1 = ybuf ? ybuf + (size_t)layer * K * 2 * F * B * N : nullptr;
     return gwtf_fwd_layer_ex(desc, layer, phase, train, 0, params, bnbuf, film, xin, first ? 1 : 0,
-                             ubuf + (size_t)layer * slot, ld, ssum, nullptr, mom_in, train ? mom_out : nullptr, s1, B, N,
-                             n_total, stream);
+                             ubuf + (size_t)layer * slot, ld, ssum, nullptr, y1, mom_in, train ? mom_out : nullptr, s1,
+                             B, N, n_total, stream);
 }
 
 int gwtf_fwd_bstat(const gwtf_stack_desc* desc, const float* params, const double* mom, const double* sum1,
@@ -297,8 +299,8 @@ int gwtf_nll_from_state(const gwtf_stack_desc* desc, const float* ubuf, const fl
 
 int gwtf_fwd_all(const gwtf_stack_desc* desc, int32_t train, const float* params, const float* bnbuf,
                  const float* film, const float* points, const float* base, const float* logw, float* ubuf, float* ld,
-                 float* ssum, double* mom, double* sum1, float* bstat, int32_t B, int32_t N, float* nll, float* logp,
-                 void* stream) {
+                 float* ssum, float* ybuf, double* mom, double* sum1, float* bstat, int32_t B, int32_t N, float* nll,
+                 float* logp, void* stream) {
     if (int rc = check_desc(desc)) return rc;
     if (!ubuf || !ld) return fail(-10, "null pointer argument");
     if (B <= 0 || N <= 0) return 0;
@@ -315,10 +317,10 @@ int gwtf_fwd_all(const gwtf_stack_desc* desc, int32_t train, const float* params
     }
     for (int l = L - 1; l >= 0; --l) {
         if (train)
-            if (int rc = gwtf_fwd_layer(desc, l, 0, 1, params, bnbuf, film, points, ubuf, ld, ssum, mom, sum1, B, N,
-                                        n_total, stream)) return rc;
-        if (int rc = gwtf_fwd_layer(desc, l, 1, train, params, bnbuf, film, points, ubuf, ld, ssum, mom, sum1, B, N,
-                                    n_total, stream)) return rc;
+            if (int rc = gwtf_fwd_layer(desc, l, 0, 1, params, bnbuf, film, points, ubuf, ld, ssum, ybuf, mom, sum1, B,
+                                        N, n_total, stream)) return rc;
+        if (int rc = gwtf_fwd_layer(desc, l, 1, train, params, bnbuf, film, points, ubuf, ld, ssum, ybuf, mom, sum1, B,
+                                    N, n_total, stream)) return rc;
     }
     if (train && bstat)
         if (int rc = gwtf_fwd_bstat(desc, params, mom, sum1, n_total, bstat, stream)) return rc;

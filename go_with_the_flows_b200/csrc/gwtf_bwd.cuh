@@ -59,6 +59,7 @@ struct BwdArgs {
     const float* xin;        // input of the layer: (K,B,3,N) or the (B,3,N) data cloud
     int xin_shared;
     const float* xout;       // output of the layer = ubuf[layer] (K,B,3,N)
+    const float* y1in;       // (K,2,F,B,N) kept by the forward apply pass, or null: recompute h1
     const double* mom_in;    // (K,16) moments of the layer input
     const double* sum1;      // (K,2,2,F)
     double* bsum;            // (K,2,4,F) this layer: sum dn1 | sum dn1*n1 | sum dy0 | sum dy0*hhat0
@@ -255,7 +256,8 @@ __global__ void __launch_bounds__(kThreads) k_bwd_layer_d(const BwdArgs a) {
 #pragma unroll
         for (int net = 1; net >= 0; --net) {
             float acc[P][FP];
-            contract_h1<FP, P>(S.W, net, F, x, acc);
+            if (a.y1in) load_h1<FP, P, kThreads>(S.W, net, F, acc, a.y1in + (size_t)j * 2 * F * B * N, B, N, b, n0, tid, valid);
+            else contract_h1<FP, P>(S.W, net, F, x, acc);
             if (net == 1) {
                 float olv[P][3];
                 head_out<FP, P>(S.W, 1, acc, olv);
@@ -413,7 +415,8 @@ __global__ void __launch_bounds__(kThreads) k_bwd_layer_e(const BwdArgs a) {
                 }
             }
             float acc[P][FP];
-            contract_h1<FP, P>(S.W, net, F, x, acc);
+            if (a.y1in) load_h1<FP, P, kThreads>(S.W, net, F, acc, a.y1in + (size_t)j * 2 * F * B * N, B, N, b, n0, tid, valid);
+            else contract_h1<FP, P>(S.W, net, F, x, acc);
             // h1 -> dh1 in place
 #pragma unroll
             for (int f = 0; f < FP; ++f) {

@@ -291,6 +291,47 @@ __device__ __forceinline__ void head_out(const LayerW<FP>& W, int net, const flo
     }
 }
 
+// y1 = st.x*h1 + st.y of both nets is kept from the apply pass ([net][f][b][n], coalesced over n) so the
+// backward phases need not recompute the F x F contraction: h1 = (y1 - st.y) / st.x.
+template <int FP, int P, int TT, class WT>
+__device__ __forceinline__ void store_y1(const WT& W, int net, int F, const float (&acc)[P][FP], float* y1, int B,
+                                         int N, int b, int n0, int tid, const bool (&valid)[P]) {
+#pragma unroll
+    for (int f = 0; f < FP; ++f) {
+        if (f < F) {
+            const float2 st = W.st[net][f];
+            float* dst = y1 + (((size_t)net * F + f) * B + b) * N;
+#pragma unroll
+            for (int p = 0; p < P; ++p)
+                if (valid[p]) dst[n0 + p * TT + tid] = fmaf(st.x, acc[p][f], st.y);
+        }
+    }
+}
+template <int FP, int P, int TT, class WT>
+__device__ __forceinline__ void load_h1(const WT& W, int net, int F, float (&acc)[P][FP], const float* y1, int B, int N,
+                                        int b, int n0, int tid, const bool (&valid)[P]) {
+    // every load is unconditional on a clamped (always valid) address so that all P*FP of them are
+    // in flight together; padding channels / points are zeroed afterwards
+    const float* base = y1 + ((size_t)net * F * B + b) * N;
+    const size_t fstride = (size_t)B * N;
+    int idx[P];
+#pragma unroll
+    for (int p = 0; p < P; ++p) idx[p] = min(n0 + p * TT + tid, N - 1);
+#pragma unroll
+    for (int f = 0; f < FP; ++f) {
+        const float* src = base + (size_t)min(f, F - 1) * fstride;
+#pragma unroll
+        for (int p = 0; p < P; ++p) acc[p][f] = __ldg(src + idx[p]);
+    }
+#pragma unroll
+    for (int f = 0; f < FP; ++f) {
+        const float2 st = W.st[net][f];
+        const float inv = f < F ? 1.0f / st.x : 0.f;
+#pragma unroll
+        for (int p = 0; p < P; ++p) acc[p][f] = (valid[p] && f < F) ? (acc[p][f] - st.y) * inv : 0.f;
+    }
+}
+
 __device__ __forceinline__ float softsign(float v) { return v / (1.0f + fabsf(v)); }
 
 // flows.py:113/115 on all three dims (kept dims see mu = logvar = 0 exactly).

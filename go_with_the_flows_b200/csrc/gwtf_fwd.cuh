@@ -155,6 +155,7 @@ struct LayerArgs {
     float* ld;              // (K,B,N) running sum of logvar over dims and layers (+=), may be null
     float* ssum;            // (K,B,3,N) per-dim running sum (+=), may be null
     float* trio;            // (K,3,B,3,N): p_out | mu | logvar of this layer, may be null
+    float* y1out;           // (K,2,F,B,N): post-FiLM pre-activation of sd1 kept for backward, may be null
     const double* mom_in;   // (K,16) moments of this layer's input
     double* mom_out;        // (K,16) moments of this layer's output (+=), may be null
     double* sum1;           // (K,2,2,F)
@@ -257,11 +258,13 @@ __global__ void __launch_bounds__(kThreads) k_fwd_layer(const LayerArgs a) {
                 float acc[P][FP];
                 contract_h1<FP, P>(S.W, 0, F, x, acc);
                 head_out<FP, P>(S.W, 0, acc, omu);
+                if (a.y1out) store_y1<FP, P, kThreads>(S.W, 0, F, acc, a.y1out + (size_t)j * 2 * F * B * N, B, N, b, n0, tid, valid);
             }
             {
                 float acc[P][FP];
                 contract_h1<FP, P>(S.W, 1, F, x, acc);
                 head_out<FP, P>(S.W, 1, acc, olv);
+                if (a.y1out) store_y1<FP, P, kThreads>(S.W, 1, F, acc, a.y1out + (size_t)j * 2 * F * B * N, B, N, b, n0, tid, valid);
             }
             float v[32];
 #pragma unroll

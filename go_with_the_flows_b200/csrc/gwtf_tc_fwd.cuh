@@ -18,6 +18,17 @@
 
 namespace gwtf {
 
+#ifdef GWTF_TIMING
+__device__ long long g_tc_cycles[16];
+#define GWTF_T(i) do { if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) { long long c_ = clock64(); g_tc_cycles[i] += c_ - t_last_; t_last_ = c_; } } while (0)
+#define GWTF_T0() long long t_last_ = clock64()
+#define GWTF_RT(i) do {} while (0)
+#else
+#define GWTF_RT(i) do {} while (0)
+#define GWTF_T(i) do {} while (0)
+#define GWTF_T0() do {} while (0)
+#endif
+
 constexpr int kTcThreads = 128;
 constexpr int kTcCols = 128;          // TMEM columns per CTA
 
@@ -131,11 +142,16 @@ __device__ __forceinline__ void issue_ss_k8(uint32_t d_tmem, const float* x_hi, 
 // all threads: relu the accumulator row of this thread and write it back as the next A operand
 // (all FPK columns are loaded in one go so the TMEM read latency is paid once, not per chunk)
 template <int FPK, int FPN>
-__device__ __forceinline__ void relu_to_operand(uint32_t trow) {
+__device__ __forceinline__ void relu_to_operand(uint32_t trow, float* keep = nullptr, size_t keep_stride = 0, int F = 0) {
     using C = TcCols<FPK, FPN>;
     float y[FPK];
     tmem_ld<FPK>(trow + C::D, y);
     tmem_wait_ld();
+    if (keep) {     // y1 of this thread's point, one coalesced store per channel
+#pragma unroll
+        for (int f = 0; f < FPK; ++f)
+            if (f < F) keep[(size_t)f * keep_stride] = y[f];
+    }
 #pragma unroll
     for (int c = 0; c < FPK; c += 8) {
         float hi[8], lo[8];
@@ -190,8 +206,10 @@ __device__ __forceinline__ void run_to_h1(TcFwdSmem<FPK, FPN>& S, int net, uint3
         tc_commit(&S.bar_mma);
     }
     tc_wait(&S.bar_mma, phase);
+    GWTF_RT(11);
     relu_to_operand<FPK, FPN>(trow);
     tc_handoff();
+    GWTF_RT(12);
     if (tid == 0) {
         tc_fence_after();
         issue_ts<FPK, FPN>(tbase + C::D, tbase + C::Ahi, tbase + C::Alo, S.ops[net].B1.hi, S.ops[net].B1.lo);
@@ -222,6 +240,7 @@ __global__ void __launch_bounds__(kTcThreads) k_fwd_layer_tc(const LayerArgs a) 
     src.sum1 = a.sum1 ? a.sum1 + (size_t)j * 4 * F : nullptr;
     src.n_total = a.n_total;
 
+    GWTF_T0();
     if (warp == 0) tmem_alloc(&S.tmem_base, kTcCols);
     if (tid == 0) { mbar_init(&S.bar_tma, 1); mbar_init(&S.bar_mma, 1); mbar_fence_init(); }
     for (int i = tid; i < 2 * (2 * FPN + 32); i += TT) (&S.red[0][0])[i] = 0.f;
@@ -230,9 +249,11 @@ __global__ void __launch_bounds__(kTcThreads) k_fwd_layer_tc(const LayerArgs a) 
     __syncthreads();
     if (tid == 0) issue_layer_copy(raw, src, F, !train, false, &S.bar_tma);
     mbar_wait(&S.bar_tma, 0u);
+    GWTF_T(0);
     stage_vectors<FPN, false>(S.W, (LayerWB<FPN>*)nullptr, raw, src, F, a.d.warp_mask[l], train, PHASE == 0, nullptr,
                               tid, TT);
     __syncthreads();
+    GWTF_T(1);
     const NetOffsets o = net_offsets(F, popc3(a.d.warp_mask[l]));
 #pragma unroll
     for (int net = 0; net < 2; ++net) {
@@ -244,6 +265,7 @@ __global__ void __launch_bounds__(kTcThreads) k_fwd_layer_tc(const LayerArgs a) 
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    GWTF_T(2);
     const uint32_t tbase = S.tmem_base;
     const uint32_t trow = tbase + ((uint32_t)(warp * 32) << 16);
     uint32_t mma_phase = 0u;
@@ -268,6 +290,7 @@ __global__ void __launch_bounds__(kTcThreads) k_fwd_layer_tc(const LayerArgs a) 
             for (int net = 0; net < 2; ++net)
                 stage_b1<FPK, FPN>(S.ops[net], raw + net * o.stride + o.W1, S.W.st[net], F, tid, TT);
             cur_b = b;
+            GWTF_T(3);
         }
         float x[3];
         const float* xin = a.xin_shared ? a.xin + (size_t)b * 3 * N : a.xin + ((size_t)j * B + b) * 3 * N;
@@ -276,11 +299,13 @@ __global__ void __launch_bounds__(kTcThreads) k_fwd_layer_tc(const LayerArgs a) 
         write_x_operand(S.x_hi, S.x_lo, x, tid);
         fence_proxy_async();
         tc_handoff();
+        GWTF_T(4);
 
         if (PHASE == 0) {
 #pragma unroll 1
             for (int net = 0; net < 2; ++net) {
                 run_to_h1<FPK, FPN>(S, net, tbase, trow, mma_phase, tid);
+                GWTF_T(5);
                 // per-channel sum h1, sum h1^2: 16 channels -> 32 values per warp reduce-scatter
                 float h[FPN];
                 tmem_ld<FPN>(trow + C::D, h);
@@ -298,25 +323,31 @@ __global__ void __launch_bounds__(kTcThreads) k_fwd_layer_tc(const LayerArgs a) 
                     atomicAdd(&S.red[net][2 * c + lane], r);
                 }
                 tc_handoff();      // every thread is done with the accumulator before the next MMA0
+                GWTF_T(6);
             }
         } else {
             float o3[2][3];
 #pragma unroll 1
             for (int net = 0; net < 2; ++net) {
                 run_to_h1<FPK, FPN>(S, net, tbase, trow, mma_phase, tid);
-                relu_to_operand<FPK, FPN>(trow);
+                GWTF_T(5);
+                relu_to_operand<FPK, FPN>(trow, (a.y1out && valid) ? a.y1out + ((((size_t)j * 2 + net) * F) * B + b) * N + n : nullptr,
+                                          (size_t)B * N, F);
                 tc_handoff();
+                GWTF_T(7);
                 if (tid == 0) {
                     tc_fence_after();
                     issue_ts<FPK, 16>(tbase + C::D, tbase + C::Ahi, tbase + C::Alo, S.ops[net].B2.hi, S.ops[net].B2.lo);
                     tc_commit(&S.bar_mma);
                 }
                 tc_wait(&S.bar_mma, mma_phase);
+                GWTF_T(8);
                 float ov[8];
                 tmem_ld8(trow + C::D, ov);
                 tmem_wait_ld();
                 o3[net][0] = ov[0]; o3[net][1] = ov[1]; o3[net][2] = ov[2];
                 tc_handoff();
+                GWTF_T(9);
             }
             float lam[3];
             if (a.direct) warp_point<true>(x, o3[0], o3[1], lam);
@@ -347,6 +378,7 @@ __global__ void __launch_bounds__(kTcThreads) k_fwd_layer_tc(const LayerArgs a) 
                 v[6] = x[1] * x[1]; v[7] = x[1] * x[2]; v[8] = x[2] * x[2];
             }
             if (a.mom_out) macc += warp_reduce_scatter32(v, lane);
+            GWTF_T(10);
         }
     }
     // ---- flush block partials

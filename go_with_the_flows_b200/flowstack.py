@@ -131,6 +131,10 @@ class FlowStack:
                 mask |= 1 << d
             self.desc.warp_mask[l] = mask
         self.sync_gradients = True
+        # keep y1 (296 B per point/component/layer at F=37) from the apply pass so that backward skips one
+        # contraction per phase; measured SLOWER than recomputing on B200 (r01: 309/429 us vs 214/380 us per
+        # backward launch), so it is off by default
+        self.keep_activations = False
         self.C = self.K * self.L * 4
         if self.flat:
             self._build_layout()
@@ -459,13 +463,20 @@ class _StackNLLPass(torch.autograd.Function):
         ld = torch.zeros(K, B, N, device=dev)
         mom = sum1 = bstat = None
         n_total = float(B * N)
+        # y1 of every layer/net kept for backward (skips one F x F contraction in each backward phase)
+        ybuf = None
+        if stack.keep_activations:
+            need = L * K * 2 * Fd * B * N * 4
+            free, _ = torch.cuda.mem_get_info(dev)
+            if need < 0.5 * free + torch.cuda.memory_reserved(dev) - torch.cuda.memory_allocated(dev):
+                ybuf = torch.empty(L, K, 2, Fd, B, N, device=dev)
         if training:
             mom = torch.zeros(L, K, nat.MOM_STRIDE, device=dev, dtype=torch.float64)
             sum1 = torch.zeros(L, K, 2, 2, Fd, device=dev, dtype=torch.float64)
             bstat = torch.empty(L, K, 2, 4, Fd, device=dev)
         if not sync:
             nat.check(lib.gwtf_fwd_all(desc, int(training), nat.ptr(params), nat.ptr(bnbuf), nat.ptr(film), nat.ptr(p),
-                                       None, None, nat.ptr(ubuf), nat.ptr(ld), nat.ptr(ssum), nat.ptr(mom),
+                                       None, None, nat.ptr(ubuf), nat.ptr(ld), nat.ptr(ssum), nat.ptr(ybuf), nat.ptr(mom),
                                        nat.ptr(sum1), nat.ptr(bstat), B, N, None, None, st), 'gwtf_fwd_all')
         else:
             cnt = torch.tensor([n_total], device=dev, dtype=torch.float64)
@@ -476,8 +487,8 @@ class _StackNLLPass(torch.autograd.Function):
                 dist.all_reduce(mom[l])
                 for phase in (0, 1):
                     nat.check(lib.gwtf_fwd_layer(desc, l, phase, 1, nat.ptr(params), nat.ptr(bnbuf), nat.ptr(film),
-                                                 nat.ptr(p), nat.ptr(ubuf), nat.ptr(ld), nat.ptr(ssum), nat.ptr(mom),
-                                                 nat.ptr(sum1), B, N, n_total, st), 'gwtf_fwd_layer')
+                                                 nat.ptr(p), nat.ptr(ubuf), nat.ptr(ld), nat.ptr(ssum), nat.ptr(ybuf),
+                                                 nat.ptr(mom), nat.ptr(sum1), B, N, n_total, st), 'gwtf_fwd_layer')
                     if phase == 0:
                         dist.all_reduce(sum1[l])
             nat.check(lib.gwtf_fwd_bstat(desc, nat.ptr(params), nat.ptr(mom), nat.ptr(sum1), n_total, nat.ptr(bstat),
@@ -489,6 +500,7 @@ class _StackNLLPass(torch.autograd.Function):
         # running stats are updated in place right after a train-mode forward (and are not read by
         # the train-mode backward), so they must not go through save_for_backward's version check
         ctx.bnbuf = bnbuf
+        ctx.ybuf = ybuf
         ctx.save_for_backward(p, params, film, ubuf, mom, sum1)
         z = ubuf[0]
         ctx.mark_non_differentiable(*([bstat] if bstat is not None else []))
@@ -500,6 +512,7 @@ class _StackNLLPass(torch.autograd.Function):
         stack = ctx.stack
         p, params, film, ubuf, mom, sum1 = ctx.saved_tensors
         bnbuf = ctx.bnbuf
+        ybuf = ctx.ybuf
         K, L, Fd = stack.K, stack.L, stack.F
         B, _, N = p.shape
         dev = p.device
@@ -515,14 +528,14 @@ class _StackNLLPass(torch.autograd.Function):
         train = int(ctx.training)
         if not ctx.sync:
             nat.check(lib.gwtf_bwd_all(desc, train, nat.ptr(params), nat.ptr(bnbuf), nat.ptr(film), nat.ptr(p),
-                                       None, None, nat.ptr(ubuf), None, nat.ptr(mom), nat.ptr(sum1), None, None,
+                                       None, None, nat.ptr(ubuf), nat.ptr(ybuf), None, nat.ptr(mom), nat.ptr(sum1), None, None,
                                        nat.ptr(bsum), nat.ptr(gbuf), nat.ptr(gs), nat.ptr(dobuf), nat.ptr(dparams),
                                        nat.ptr(dfilm), None, None, nat.ptr(dpoints), B, N, st), 'gwtf_bwd_all')
         else:
             for l in range(L):
                 for phase in (0, 1):
                     nat.check(lib.gwtf_bwd_layer(desc, l, phase, train, nat.ptr(params), nat.ptr(bnbuf),
-                                                 nat.ptr(film), nat.ptr(p), nat.ptr(ubuf), nat.ptr(mom),
+                                                 nat.ptr(film), nat.ptr(p), nat.ptr(ubuf), nat.ptr(ybuf), nat.ptr(mom),
                                                  nat.ptr(sum1), nat.ptr(bsum), nat.ptr(gbuf), nat.ptr(gs),
                                                  nat.ptr(dobuf), nat.ptr(dparams), nat.ptr(dfilm), B, N,
                                                  ctx.n_total, st), 'gwtf_bwd_layer')
@@ -683,7 +696,7 @@ def run_module_stack(stack, p, g, mode, training):
             xout = trio[l, 0]
             nat.check(lib.gwtf_fwd_layer_ex(desc, l, phase, int(training), int(mode == 'direct'), nat.ptr(params),
                                             nat.ptr(bnbuf), nat.ptr(film), nat.ptr(cur), 1, nat.ptr(xout), None, None,
-                                            nat.ptr(trio[l]), nat.ptr(mom[l]) if training else None,
+                                            nat.ptr(trio[l]), None, nat.ptr(mom[l]) if training else None,
                                             nat.ptr(mom[nxt]) if (training and nxt is not None) else None,
                                             nat.ptr(sum1[l]) if training else None, B, N, n_total, st),
                       'gwtf_fwd_layer_ex')

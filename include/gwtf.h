@@ -26,6 +26,9 @@
  *   logw    [B][K]               NORMALISED log mixture weights (losses.py:101-104)
  *   ubuf    [L][K][B][3][N]      slot l = OUTPUT of layer l in the NLL (inverse) pass = input of
  *                                layer l-1; slot 0 = base-space sample z  (kept for backward)
+ *   ybuf    [L][K][2][F][B][N]   (optional) y1 = FiLM(BN1(sd1(.)) pre-activation of both nets kept by the apply
+ *                                pass so that backward skips one F x F contraction per phase (296 B per
+ *                                point/component/layer at F=37; pass NULL to recompute instead)
  *   mom     [L][K][16] double    sum x_d (3), sum x_d x_e (6, upper triangle) of layer l's input
  *   sum1    [L][K][2][2][F] dbl  sum h1, sum h1^2 per net/channel (BatchNorm statistics of sd1_bn)
  *   bstat   [L][K][2][4][F]      batch mean0 | biased var0 | mean1 | biased var1 actually used
@@ -90,14 +93,14 @@ int gwtf_fwd_moments(const gwtf_stack_desc* desc, const float* points, int32_t B
                      double* mom, void* stream);
 int gwtf_fwd_layer(const gwtf_stack_desc* desc, int32_t layer, int32_t phase, int32_t train,
                    const float* params, const float* bnbuf, const float* film, const float* points,
-                   float* ubuf, float* ld, float* ssum, double* mom, double* sum1,
+                   float* ubuf, float* ld, float* ssum, float* ybuf, double* mom, double* sum1,
                    int32_t B, int32_t N, double n_total, void* stream);
 /* explicit-pointer form of gwtf_fwd_layer: `xin` is (K,B,3,N), or the (B,3,N) data cloud when
  * xin_shared=1; direct=1 applies flows.py:113 instead of :115; `trio` (K,3,B,3,N), if given,
  * receives (p_out, mu, logvar) of the layer -- the per-module list API is built on this. */
 int gwtf_fwd_layer_ex(const gwtf_stack_desc* desc, int32_t layer, int32_t phase, int32_t train, int32_t direct,
                       const float* params, const float* bnbuf, const float* film, const float* xin,
-                      int32_t xin_shared, float* xout, float* ld, float* ssum, float* trio,
+                      int32_t xin_shared, float* xout, float* ld, float* ssum, float* trio, float* y1out,
                       const double* mom_in, double* mom_out, double* sum1, int32_t B, int32_t N,
                       double n_total, void* stream);
 int gwtf_fwd_bstat(const gwtf_stack_desc* desc, const float* params, const double* mom,
@@ -107,7 +110,7 @@ int gwtf_nll_from_state(const gwtf_stack_desc* desc, const float* ubuf, const fl
                         float* nll, float* logp, void* stream);
 int gwtf_fwd_all(const gwtf_stack_desc* desc, int32_t train, const float* params, const float* bnbuf,
                  const float* film, const float* points, const float* base, const float* logw,
-                 float* ubuf, float* ld, float* ssum, double* mom, double* sum1, float* bstat,
+                 float* ubuf, float* ld, float* ssum, float* ybuf, double* mom, double* sum1, float* bstat,
                  int32_t B, int32_t N, float* nll, float* logp, void* stream);
 
 /* ---- backward (autograd of everything above)
@@ -128,7 +131,7 @@ int gwtf_bwd_seed(const gwtf_stack_desc* desc, const float* ubuf, const float* l
                   float* gbuf, float* gs, float* dbase, float* dlogw, void* stream);
 int gwtf_bwd_layer(const gwtf_stack_desc* desc, int32_t layer, int32_t phase, int32_t train,
                    const float* params, const float* bnbuf, const float* film, const float* points,
-                   const float* ubuf, const double* mom, const double* sum1, double* bsum,
+                   const float* ubuf, const float* ybuf, const double* mom, const double* sum1, double* bsum,
                    float* gbuf, const float* gs, float* dobuf, float* dparams, float* dfilm,
                    int32_t B, int32_t N, double n_total, void* stream);
 int gwtf_bwd_finish(const gwtf_stack_desc* desc, int32_t train, const float* params,
@@ -137,7 +140,7 @@ int gwtf_bwd_finish(const gwtf_stack_desc* desc, int32_t train, const float* par
                     double n_total, void* stream);
 int gwtf_bwd_all(const gwtf_stack_desc* desc, int32_t train, const float* params, const float* bnbuf,
                  const float* film, const float* points, const float* base, const float* logw,
-                 const float* ubuf, const float* ld, const double* mom, const double* sum1,
+                 const float* ubuf, const float* ybuf, const float* ld, const double* mom, const double* sum1,
                  const float* nll, const float* dnll, double* bsum, float* gbuf, float* gs,
                  float* dobuf, float* dparams, float* dfilm, float* dbase, float* dlogw,
                  float* dpoints, int32_t B, int32_t N, void* stream);

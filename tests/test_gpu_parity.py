@@ -194,3 +194,23 @@ def test_two_gpu_syncbn_equals_concatenated_batch():
                           os.path.join(root, 'tests', 'dist_gpu_parity.py')], capture_output=True, text=True,
                          timeout=600)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+
+
+def test_kept_activations_path_matches():
+    """Optional path: y1 kept by the apply pass instead of recomputed in backward."""
+    gd = Golden('small_free_learned')
+    noise = parity.oracle_fp32_errors(gd, 'train')
+    import go_with_the_flows_b200.flowstack as fs
+    orig = fs.FlowStack.__init__
+
+    def patched(self, *a, **k):
+        orig(self, *a, **k)
+        self.keep_activations = True
+    fs.FlowStack.__init__ = patched
+    try:
+        res = parity.dropin_nll_errors(gd, 'train', fused_nll=True)
+    finally:
+        fs.FlowStack.__init__ = orig
+    assert res['dparams'] < max(GRAD_TOL, 3 * noise['dparams']), res
+    assert res['dg'] < max(GRAD_TOL, 3 * noise['dg']), res
+    assert res['dp'] < max(GRAD_TOL, 3 * noise['dp']), res
