@@ -282,6 +282,11 @@ def main():
     p_dev, g_dev = p_host.to(dev), g_host.to(dev)
     loss_host = torch.zeros((), pin_memory=True)
     params_all = [q for q in model.parameters()]
+    stack.prepare()
+    owned = set()
+    for name in stack.grad_masters:          # decoder tensors: averaged across ranks inside backward
+        owned.update(id(q) for q in stack.masters[name].params)
+    params_other = [q for q in params_all if id(q) not in owned]
     flush_buf = torch.empty(256 * 1024 * 1024 // 4, device=dev)
 
     def step(p, g):
@@ -292,7 +297,7 @@ def main():
         pnll = loss_fn(out_dec, logits)
         pnll.backward()
         if world > 1:
-            grads = [q.grad for q in params_all if q.grad is not None]
+            grads = [q.grad for q in params_other if q.grad is not None]
             flat = torch._utils._flatten_dense_tensors(grads)
             dist.all_reduce(flat)
             flat.div_(world)

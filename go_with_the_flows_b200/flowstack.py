@@ -131,6 +131,7 @@ class FlowStack:
                 mask |= 1 << d
             self.desc.warp_mask[l] = mask
         self.sync_gradients = True
+        self._n_total_cache = {}
         # keep y1 (296 B per point/component/layer at F=37) from the apply pass so that backward skips one
         # contraction per phase; measured SLOWER than recomputing on B200 (r01: 309/429 us vs 214/380 us per
         # backward launch), so it is off by default
@@ -275,6 +276,16 @@ class FlowStack:
             if ms.tensor.grad is not None and ms.current(ms.members[0]).grad is None:
                 ms.tensor.grad = None
                 ms.grad_views = None
+
+    def global_points(self, B, N, dev):
+        """Number of points the SyncBN statistics run over (sum of B*N over ranks).  The all-reduced
+        count needs a host read, so it is cached per local shape (ranks keep their batch sizes)."""
+        key = (B, N, _world())
+        if key not in self._n_total_cache:
+            cnt = torch.tensor([float(B * N)], device=dev, dtype=torch.float64)
+            dist.all_reduce(cnt)
+            self._n_total_cache[key] = float(cnt.item())
+        return self._n_total_cache[key]
 
     def pack_params(self):
         if self.flat:
@@ -479,9 +490,7 @@ class _StackNLLPass(torch.autograd.Function):
                                        None, None, nat.ptr(ubuf), nat.ptr(ld), nat.ptr(ssum), nat.ptr(ybuf), nat.ptr(mom),
                                        nat.ptr(sum1), nat.ptr(bstat), B, N, None, None, st), 'gwtf_fwd_all')
         else:
-            cnt = torch.tensor([n_total], device=dev, dtype=torch.float64)
-            dist.all_reduce(cnt)
-            n_total = float(cnt.item())
+            n_total = stack.global_points(B, N, dev)
             nat.check(lib.gwtf_fwd_moments(desc, nat.ptr(p), B, N, nat.ptr(mom[L - 1]), st), 'gwtf_fwd_moments')
             for l in range(L - 1, -1, -1):
                 dist.all_reduce(mom[l])
@@ -682,9 +691,7 @@ def run_module_stack(stack, p, g, mode, training):
         mom = torch.zeros(L, 1, nat.MOM_STRIDE, device=dev, dtype=torch.float64)
         sum1 = torch.zeros(L, 1, 2, 2, Fd, device=dev, dtype=torch.float64)
         if sync:
-            cnt = torch.tensor([n_total], device=dev, dtype=torch.float64)
-            dist.all_reduce(cnt)
-            n_total = float(cnt.item())
+            n_total = stack.global_points(B, N, dev)
         nat.check(lib.gwtf_fwd_moments(desc, nat.ptr(p), B, N, nat.ptr(mom[order[0]]), st), 'gwtf_fwd_moments')
     cur = p
     for i, l in enumerate(order):

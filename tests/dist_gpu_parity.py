@@ -20,7 +20,10 @@ def main():
     gd = Golden('small_freevar_global')
     per = 4 // world
     sl = slice(rank * per, (rank + 1) * per)
-    model = build_dropin(gd, 'cuda').train()
+    model = build_dropin(gd, 'cuda')
+    # as the reference does before DDP (train_ae.py:152): latent-side BatchNorms (p_prior, weights
+    # encoder) become SyncBatchNorm; the decoder's own statistics are synchronised by our kernels
+    model = torch.nn.SyncBatchNorm.convert_sync_batchnorm(model).train()
     model.mode = 'training'
     p = gd.t('in/p', torch.float32, 'cuda')[sl].contiguous().requires_grad_(True)
     g = gd.t('in/g', torch.float32, 'cuda')[sl].contiguous().requires_grad_(True)
