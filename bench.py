@@ -244,6 +244,46 @@ def kernel_only_times(model, p, g, reps):
     return out
 
 
+def side_workloads(model, cfg, dev, N):
+    """Other hot-path entry points (not the headline): fused eval-mode NLL (BASELINE configs[0] shape
+    at 64 clouds) and sampling (configs[3]/[4] shape: 256 latents x N points).  CUDA-event timed."""
+    from go_with_the_flows_b200.flowstack import sample_mixture
+    out = {}
+    G = cfg['g_latent_space_size']
+    was_training = model.training
+    model.eval()
+    try:
+        with torch.no_grad():
+            p, g = synthetic(64, N, G, seed_shift=7)
+            p, g = p.to(dev), g.to(dev)
+
+            def timed(fn, reps=3):
+                fn()
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(reps):
+                    fn()
+                e1.record()
+                torch.cuda.synchronize()
+                return e0.elapsed_time(e1) / reps
+
+            ms = timed(lambda: model.decode(p, g, N))
+            out['eval_nll_fused'] = {'points_per_s': 64 * N / (ms * 1e-3), 'ms': ms, 'clouds': 64, 'points': N,
+                                     'kernel': 'k_nll_eval (one launch, fp32 FMA)'}
+            _, g2 = synthetic(256, N, G, seed_shift=9)
+            g2 = g2.to(dev)
+            stack = model.flow_stack()
+            logits = model.get_weights(g2)
+            mu_b, lv_b = model.base_gaussian(g2)
+            ms = timed(lambda: sample_mixture(stack, g2, mu_b, lv_b, logits, N, 2026, 0))
+            out['sampling'] = {'points_per_s': 256 * N / (ms * 1e-3), 'ms': ms, 'latents': 256, 'points': N,
+                               'kernel': 'k_sample (Philox draws + direct stacks, fp32 FMA)'}
+    finally:
+        model.train(was_training)
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -389,6 +429,9 @@ def main():
                                   'flops_per_point': fl_step},
                          'kernels': kernels},
             'clocks': clocks,
+            'engine': 'tcgen05 3xTF32 forward layer kernels + fp32 FMA backward / fused-eval / sampling kernels'
+                      if os.environ.get('GWTF_TC', '1') != '0' and Fd <= 39 else 'fp32 FMA kernels',
+            'extra': side_workloads(model, cfg, dev, N),
         }
         if not args.no_cpu_baseline and world == 1:
             cb, cn = 4, N

@@ -127,18 +127,23 @@ struct BwdSmem {
 };
 
 // ---- PHASE 0: d(o_mu,o_lv), FiLM + sd2 gradients, sd1_bn backward sums ------------------------
+// h1 of the thread's P points is stashed in shared memory ([f][p][tid], conflict-free) right after
+// the contraction so that the 5-sums-per-channel reduction is a ROLLED loop over groups of 6
+// channels (30 values per warp reduce-scatter): small code, no spills, and P = 4 points per thread.
 template <int FP, int P>
 __global__ void __launch_bounds__(kThreads) k_bwd_layer_d(const BwdArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     BwdSmem<FP>& S = *reinterpret_cast<BwdSmem<FP>*>(smem_raw);
     float* raw = reinterpret_cast<float*>(smem_raw + round_up((int)sizeof(BwdSmem<FP>), 16));
     const int F = a.d.n_features, K = a.d.n_components, L = a.d.n_layers;
+    float* hbuf = raw + round_up(raw_floats(F), 4);             // [FP][P][kThreads]
     const int tid = threadIdx.x, lane = tid & 31;
     const int j = blockIdx.y, l = a.layer;
     const int N = a.N, B = a.B;
     const bool train = a.train != 0;
     constexpr int NV = 5 * FP + 3;               // per net: (ds, dt, dW2 x3) per f, db2 x3
-    constexpr int NG = (NV + 31) / 32;
+    constexpr int FG = 6;                        // channels per reduce-scatter group
+    constexpr int NGF = (FP + FG - 1) / FG;
 
     LayerSrc src;
     src.params = a.params + (size_t)(j * L + l) * a.d.rec_stride;
@@ -150,7 +155,7 @@ __global__ void __launch_bounds__(kThreads) k_bwd_layer_d(const BwdArgs a) {
 
     if (tid == 0) { mbar_init(&S.bar, 1); mbar_fence_init(); }
     if (tid < 12) S.corr[tid] = 0.f;
-    for (int i = tid; i < 2 * NG * 32; i += kThreads) (&S.red[0][0])[i] = 0.f;
+    for (int i = tid; i < 2 * round_up(NV, 32); i += kThreads) (&S.red[0][0])[i] = 0.f;
     __syncthreads();
     if (tid == 0) issue_layer_copy(raw, src, F, !train, false, &S.bar);
     const bool correct = train && a.mom_prev != nullptr;
@@ -172,24 +177,10 @@ __global__ void __launch_bounds__(kThreads) k_bwd_layer_d(const BwdArgs a) {
     const NetOffsets o = net_offsets(F, w);
     int row_of_dim[3];
     { int q = 0; for (int dd = 0; dd < 3; ++dd) row_of_dim[dd] = (wm & (1u << dd)) ? q++ : -1; }
-
-    float racc[2][NG];
-#pragma unroll
-    for (int net = 0; net < 2; ++net)
-#pragma unroll
-        for (int g = 0; g < NG; ++g) racc[net][g] = 0.f;
     int cur_b = -1;
 
     auto flush = [&](int b) {
         // block partials -> FiLM grads of shape b, sd2 grads, sd1_bn backward sums
-#pragma unroll
-        for (int net = 0; net < 2; ++net)
-#pragma unroll
-            for (int g = 0; g < NG; ++g) {
-                const int idx = g * 32 + lane;
-                if (idx < NV) atomicAdd(&S.red[net][idx], racc[net][g]);
-                racc[net][g] = 0.f;
-            }
         __syncthreads();
         float* dfl = a.dfilm + ((size_t)(b * K + j) * L + l) * 4 * F;
         float* dpr = a.dparams + (size_t)(j * L + l) * a.d.rec_stride;
@@ -217,7 +208,7 @@ __global__ void __launch_bounds__(kThreads) k_bwd_layer_d(const BwdArgs a) {
             }
         }
         __syncthreads();
-        for (int i = tid; i < 2 * NG * 32; i += kThreads) (&S.red[0][0])[i] = 0.f;
+        for (int i = tid; i < 2 * round_up(NV, 32); i += kThreads) (&S.red[0][0])[i] = 0.f;
         __syncthreads();
     };
 
@@ -253,68 +244,88 @@ __global__ void __launch_bounds__(kThreads) k_bwd_layer_d(const BwdArgs a) {
                 Gc[p][d] = G[d] - (M[d * 3 + 0] * out[p][0] + M[d * 3 + 1] * out[p][1] + M[d * 3 + 2] * out[p][2]) + cc[d];
         }
         // logvar net first: its output fixes sigma, hence both d o_mu and d o_lv
-#pragma unroll
+#pragma unroll 1
         for (int net = 1; net >= 0; --net) {
-            float acc[P][FP];
-            if (a.y1in) load_h1<FP, P, kThreads>(S.W, net, F, acc, a.y1in + (size_t)j * 2 * F * B * N, B, N, b, n0, tid, valid);
-            else contract_h1<FP, P>(S.W, net, F, x, acc);
-            if (net == 1) {
-                float olv[P][3];
-                head_out<FP, P>(S.W, 1, acc, olv);
+            {
+                float acc[P][FP];
+                if (a.y1in) load_h1<FP, P, kThreads>(S.W, net, F, acc, a.y1in + (size_t)j * 2 * F * B * N, B, N, b, n0, tid, valid);
+                else contract_h1<FP, P>(S.W, net, F, x, acc);
+                if (net == 1) {
+                    float olv[P][3];
+                    head_out<FP, P>(S.W, 1, acc, olv);
 #pragma unroll
-                for (int p = 0; p < P; ++p) {
-                    const int n = n0 + p * kThreads + tid;
+                    for (int p = 0; p < P; ++p) {
+                        const int n = n0 + p * kThreads + tid;
 #pragma unroll
-                    for (int d = 0; d < 3; ++d) {
-                        const float lam = softsign(olv[p][d]);
-                        const float ex = expf(lam);
-                        const float sig2 = GWTF_FLOW_EPS + ex;
-                        const float sig = sqrtf(sig2);
-                        const float gsd = valid[p] ? a.gs[sb + (size_t)d * N + n] : 0.f;
-                        const float gd = valid[p] ? Gc[p][d] : 0.f;
-                        const float gin = gd / sig;
-                        dom[p][d] = -gin;
-                        const float dlam = gsd - gd * out[p][d] * ex / (2.0f * sig2);
-                        const float den = 1.0f + fabsf(olv[p][d]);
-                        dov[p][d] = dlam / (den * den);
-                        if (valid[p]) {
-                            a.gbuf[sb + (size_t)d * N + n] = gin;
-                            a.dobuf[((size_t)j * B + b) * 6 * N + (size_t)d * N + n] = dom[p][d];
-                            a.dobuf[((size_t)j * B + b) * 6 * N + (size_t)(3 + d) * N + n] = dov[p][d];
+                        for (int d = 0; d < 3; ++d) {
+                            const float lam = softsign(olv[p][d]);
+                            const float ex = expf(lam);
+                            const float sig2 = GWTF_FLOW_EPS + ex;
+                            const float sig = sqrtf(sig2);
+                            const float gsd = valid[p] ? a.gs[sb + (size_t)d * N + n] : 0.f;
+                            const float gd = valid[p] ? Gc[p][d] : 0.f;
+                            const float gin = gd / sig;
+                            dom[p][d] = -gin;
+                            const float dlam = gsd - gd * out[p][d] * ex / (2.0f * sig2);
+                            const float den = 1.0f + fabsf(olv[p][d]);
+                            dov[p][d] = dlam / (den * den);
+                            if (valid[p]) {
+                                a.gbuf[sb + (size_t)d * N + n] = gin;
+                                a.dobuf[((size_t)j * B + b) * 6 * N + (size_t)d * N + n] = dom[p][d];
+                                a.dobuf[((size_t)j * B + b) * 6 * N + (size_t)(3 + d) * N + n] = dov[p][d];
+                            }
                         }
                     }
                 }
-            }
-            const float (&dO)[P][3] = net == 1 ? dov : dom;
-            // 5 sums per feature + 3 bias sums, reduced 32 values at a time
 #pragma unroll
-            for (int g = 0; g < NG; ++g) {
+                for (int f = 0; f < FP; ++f)
+#pragma unroll
+                    for (int p = 0; p < P; ++p) hbuf[(f * P + p) * kThreads + tid] = acc[p][f];
+            }
+            float dO[P][3];
+#pragma unroll
+            for (int p = 0; p < P; ++p)
+#pragma unroll
+                for (int d = 0; d < 3; ++d) dO[p][d] = net == 1 ? dov[p][d] : dom[p][d];
+            // 5 sums per channel, 6 channels (30 values) per warp reduce-scatter; rolled
+#pragma unroll 1
+            for (int g = 0; g < NGF; ++g) {
                 float v[32];
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const int idx = g * 32 + i;
-                    float s = 0.f;
-                    if (idx < 5 * FP) {
-                        const int f = idx / 5, c = idx - 5 * f;
+                for (int i = 0; i < 32; ++i) v[i] = 0.f;
+#pragma unroll
+                for (int ff = 0; ff < FG; ++ff) {
+                    const int f = g * FG + ff;
+                    if (f < FP) {
                         const float2 st = S.W.st[net][f];
                         const float2 mi = S.W.mi1[net][f];
                         const float4 w2 = S.W.w2[net][f];
 #pragma unroll
                         for (int p = 0; p < P; ++p) {
-                            const float y1 = fmaf(st.x, acc[p][f], st.y);
+                            const float h = hbuf[(f * P + p) * kThreads + tid];
+                            const float y1 = fmaf(st.x, h, st.y);
                             const float da1 = w2.x * dO[p][0] + w2.y * dO[p][1] + w2.z * dO[p][2];
                             const float dy1 = y1 > 0.f ? da1 : 0.f;
-                            if (c == 0) s += dy1 * fmaf(acc[p][f], mi.y, -mi.x);
-                            else if (c == 1) s += dy1;
-                            else s += dO[p][c - 2] * fmaxf(y1, 0.f);
+                            const float a1 = fmaxf(y1, 0.f);
+                            v[ff * 5 + 0] += dy1 * fmaf(h, mi.y, -mi.x);
+                            v[ff * 5 + 1] += dy1;
+                            v[ff * 5 + 2] += dO[p][0] * a1;
+                            v[ff * 5 + 3] += dO[p][1] * a1;
+                            v[ff * 5 + 4] += dO[p][2] * a1;
                         }
-                    } else if (idx < NV) {
-#pragma unroll
-                        for (int p = 0; p < P; ++p) s += dO[p][idx - 5 * FP];
                     }
-                    v[i] = s;
                 }
-                racc[net][g] += warp_reduce_scatter32(v, lane);
+                const float r = warp_reduce_scatter32(v, lane);
+                if (lane < 5 * FG && g * 5 * FG + lane < 5 * FP) atomicAdd(&S.red[net][g * 5 * FG + lane], r);
+            }
+            {   // sd2 bias sums
+                float v[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = 0.f;
+#pragma unroll
+                for (int p = 0; p < P; ++p) { v[0] += dO[p][0]; v[1] += dO[p][1]; v[2] += dO[p][2]; }
+                const float r = warp_reduce_scatter32(v, lane);
+                if (lane < 3) atomicAdd(&S.red[net][5 * FP + lane], r);
             }
         }
     }
@@ -342,7 +353,8 @@ __global__ void __launch_bounds__(kThreads) k_bwd_layer_e(const BwdArgs a) {
     const int j = blockIdx.y, l = a.layer;
     const int N = a.N, B = a.B;
     const bool train = a.train != 0;
-    constexpr int EG = 6;                                   // e's per reduce-scatter group (5 sums each)
+    constexpr int EG = 4;                                   // e's per reduce-scatter group (5 sums each); 4 so
+                                                            // that a0 is written as one conflict-free STS.128
     constexpr int NGE = (FP + EG - 1) / EG;
     // GEMM ownership: 8x8 blocks of dW1[f][e], NQ point groups
     constexpr int FB = (FP + 7) / 8;
@@ -450,10 +462,13 @@ __global__ void __launch_bounds__(kThreads) k_bwd_layer_e(const BwdArgs a) {
 #pragma unroll 1
             for (int g = 0; g < NGE; ++g) {
                 float v[32];
+                float a0v[P][EG];
 #pragma unroll
                 for (int i = 0; i < 32; ++i) v[i] = 0.f;
 #pragma unroll
                 for (int ee = 0; ee < EG; ++ee) {
+#pragma unroll
+                    for (int p = 0; p < P; ++p) a0v[p][ee] = 0.f;
                     const int e = g * EG + ee;
                     if (e < FP) {
                         float da0[P];
@@ -477,7 +492,7 @@ __global__ void __launch_bounds__(kThreads) k_bwd_layer_e(const BwdArgs a) {
                             const float y0 = fmaf(qv.x, x[p][0], fmaf(qv.y, x[p][1], fmaf(qv.z, x[p][2], qv.w)));
                             const float dy0 = y0 > 0.f ? da0[p] : 0.f;
                             const float hh = fmaf(rv.x, x[p][0], fmaf(rv.y, x[p][1], fmaf(rv.z, x[p][2], rv.w)));
-                            A0s[(size_t)(p * kThreads + tid) * FP + e] = valid[p] ? fmaxf(y0, 0.f) : 0.f;
+                            a0v[p][ee] = valid[p] ? fmaxf(y0, 0.f) : 0.f;
                             vin[p][0] = fmaf(qv.x, dy0, vin[p][0]);
                             vin[p][1] = fmaf(qv.y, dy0, vin[p][1]);
                             vin[p][2] = fmaf(qv.z, dy0, vin[p][2]);
@@ -488,6 +503,12 @@ __global__ void __launch_bounds__(kThreads) k_bwd_layer_e(const BwdArgs a) {
                             v[ee * 5 + 4] += dy0 * x[p][2];
                         }
                     }
+                }
+                if (g * EG < FP) {
+#pragma unroll
+                    for (int p = 0; p < P; ++p)
+                        *reinterpret_cast<float4*>(A0s + (size_t)(p * kThreads + tid) * FP + g * EG) =
+                            make_float4(a0v[p][0], a0v[p][1], a0v[p][2], a0v[p][3]);
                 }
                 eacc[g] += warp_reduce_scatter32(v, lane);
             }

@@ -277,10 +277,31 @@ __global__ void __launch_bounds__(kTcThreads) k_fwd_layer_tc(const LayerArgs a) 
     const int total_tiles = B * a.tiles_per_shape;
     const int per_cta = (total_tiles + gridDim.x - 1) / gridDim.x;
     const int t_begin = blockIdx.x * per_cta, t_end = min(t_begin + per_cta, total_tiles);
+    float mv[9];                                       // per-thread moment partials of the outputs
+#pragma unroll
+    for (int i = 0; i < 9; ++i) mv[i] = 0.f;
+    // software prefetch: the next tile's coordinates (and running log-det sums) are loaded while the
+    // current tile is in the MMA chain, so their global latency is off the critical path
+    auto tile_coords = [&](int t, int& b, int& n, bool& valid) {
+        b = t / a.tiles_per_shape;
+        n = (t - b * a.tiles_per_shape) * TT + tid;
+        valid = n < N;
+    };
+    auto load_x = [&](int t, float (&x)[3], float (&s3)[3]) {
+        int b, n; bool valid;
+        tile_coords(t, b, n, valid);
+        const float* xin = a.xin_shared ? a.xin + (size_t)b * 3 * N : a.xin + ((size_t)j * B + b) * 3 * N;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            x[d] = valid ? xin[(size_t)d * N + n] : 0.f;
+            s3[d] = (PHASE == 1 && a.ssum && valid) ? a.ssum[((size_t)j * B + b) * 3 * N + (size_t)d * N + n] : 0.f;
+        }
+    };
+    float xn[3], sn[3];
+    if (t_begin < t_end) load_x(t_begin, xn, sn);
     for (int t = t_begin; t < t_end; ++t) {
-        const int b = t / a.tiles_per_shape;
-        const int n = (t - b * a.tiles_per_shape) * TT + tid;
-        const bool valid = n < N;
+        int b, n; bool valid;
+        tile_coords(t, b, n, valid);
         if (PHASE == 1 && b != cur_b) {
             __syncthreads();
             stage_film<FPN, false>(S.W, (LayerWB<FPN>*)nullptr, a.film + ((size_t)(b * K + j) * L + l) * 4 * F, F, tid,
@@ -292,14 +313,14 @@ __global__ void __launch_bounds__(kTcThreads) k_fwd_layer_tc(const LayerArgs a) 
             cur_b = b;
             GWTF_T(3);
         }
-        float x[3];
-        const float* xin = a.xin_shared ? a.xin + (size_t)b * 3 * N : a.xin + ((size_t)j * B + b) * 3 * N;
+        float x[3], s3[3];
 #pragma unroll
-        for (int d = 0; d < 3; ++d) x[d] = valid ? xin[(size_t)d * N + n] : 0.f;
+        for (int d = 0; d < 3; ++d) { x[d] = xn[d]; s3[d] = sn[d]; }
         write_x_operand(S.x_hi, S.x_lo, x, tid);
         fence_proxy_async();
         tc_handoff();
         GWTF_T(4);
+        if (t + 1 < t_end) load_x(t + 1, xn, sn);
 
         if (PHASE == 0) {
 #pragma unroll 1
@@ -352,9 +373,6 @@ __global__ void __launch_bounds__(kTcThreads) k_fwd_layer_tc(const LayerArgs a) 
             float lam[3];
             if (a.direct) warp_point<true>(x, o3[0], o3[1], lam);
             else warp_point<false>(x, o3[0], o3[1], lam);
-            float v[32];
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = 0.f;
             if (valid) {
                 const size_t base = ((size_t)j * B + b) * 3 * N + n;
 #pragma unroll
@@ -362,7 +380,7 @@ __global__ void __launch_bounds__(kTcThreads) k_fwd_layer_tc(const LayerArgs a) 
                 if (a.ld) a.ld[((size_t)j * B + b) * N + n] += lam[0] + lam[1] + lam[2];
                 if (a.ssum)
 #pragma unroll
-                    for (int d = 0; d < 3; ++d) a.ssum[base + (size_t)d * N] += lam[d];
+                    for (int d = 0; d < 3; ++d) a.ssum[base + (size_t)d * N] = s3[d] + lam[d];
                 if (a.trio) {
                     const size_t tb = (((size_t)j * 3) * B + b) * 3 * N + n;
                     const size_t ts = (size_t)B * 3 * N;
@@ -373,13 +391,18 @@ __global__ void __launch_bounds__(kTcThreads) k_fwd_layer_tc(const LayerArgs a) 
                         a.trio[tb + 2 * ts + (size_t)d * N] = lam[d];
                     }
                 }
-                v[0] = x[0]; v[1] = x[1]; v[2] = x[2];
-                v[3] = x[0] * x[0]; v[4] = x[0] * x[1]; v[5] = x[0] * x[2];
-                v[6] = x[1] * x[1]; v[7] = x[1] * x[2]; v[8] = x[2] * x[2];
+                mv[0] += x[0]; mv[1] += x[1]; mv[2] += x[2];
+                mv[3] += x[0] * x[0]; mv[4] += x[0] * x[1]; mv[5] += x[0] * x[2];
+                mv[6] += x[1] * x[1]; mv[7] += x[1] * x[2]; mv[8] += x[2] * x[2];
             }
-            if (a.mom_out) macc += warp_reduce_scatter32(v, lane);
             GWTF_T(10);
         }
+    }
+    if (PHASE == 1 && a.mom_out) {
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = i < 9 ? mv[i] : 0.f;
+        macc = warp_reduce_scatter32(v, lane);
     }
     // ---- flush block partials
     __syncthreads();
