@@ -40,7 +40,7 @@ def _world():
 
 class _LayerRef:
     """Direct references to the tensors of one coupling layer, in record order."""
-    __slots__ = ('module', 'warp', 'point', 'cond', 'bn_point', 'bn_cond')
+    __slots__ = ('module', 'warp', 'point', 'cond', 'bn_point')
 
     def __init__(self, m):
         self.module = m
@@ -48,7 +48,6 @@ class _LayerRef:
         self.point = []      # parameters in record order
         self.bn_point = []   # (bn0, bn1) per net
         self.cond = []       # per net, per (w, b): (lin0, bn, lin1)
-        self.bn_cond = []
         for X in ('mu', 'logvar'):
             t0 = getattr(m, 'T_%s_0' % X)
             t1 = getattr(m, 'T_%s_1' % X)
@@ -108,6 +107,7 @@ class FlowStack:
         (the per-module list API) leaves the module tensors where they are and gathers them per
         call instead -- only one stack may own the storage of a given set of modules."""
         self.flat = own_storage
+        self._components = components
         self.K = len(components)
         self.L = len(components[0])
         assert all(len(c) == self.L for c in components)
@@ -264,9 +264,24 @@ class FlowStack:
             for prm, v in zip(ms.params, ms.grad_views):
                 prm.grad = v
 
+    def _modules_replaced(self):
+        """True when a BatchNorm of the stack was swapped for another module object after this stack was
+        built (torch.nn.SyncBatchNorm.convert_sync_batchnorm, train_ae.py:152, creates new modules that
+        share the old tensors)."""
+        for comp in (self._components[0], self._components[-1]):
+            for m in (comp[0], comp[-1]):
+                ref = self.layers[self._components.index(comp)][comp.index(m)]
+                if m.T_mu_0[1] is not ref.bn_point[0][0] or m.T_logvar_0_cond_b[1] is not ref.cond[3][1]:
+                    return True
+        return False
+
     def prepare(self):
         """Called at the top of every pass: keep the flat storage valid and honour
         `optimizer.zero_grad(set_to_none=True)` (parameters lost their .grad -> clear the masters)."""
+        if self._modules_replaced():
+            self.layers = [[_LayerRef(m) for m in comp] for comp in self._components]
+            if self.flat:
+                self._build_layout()
         if not self.flat:
             return
         if not self._is_flat():
@@ -656,9 +671,6 @@ def sample_mixture(stack, g, mu_base, lv_base, logits, n_points, seed, stream_id
     return samples, labels, z
 
 
-_warned_list_api = [False]
-
-
 @torch.no_grad()
 def run_module_stack(stack, p, g, mode, training):
     """Per-module list API (flows.py:117,160; decoders.py:79) on a K=1 stack: every layer's
@@ -669,8 +681,6 @@ def run_module_stack(stack, p, g, mode, training):
         raise nat.GwtfError('the flow stack runs on CUDA tensors only (got %s)' % p.device)
     if mode not in ('direct', 'inverse'):
         raise ValueError(mode)
-    if torch.is_grad_enabled() and not _warned_list_api[0]:
-        pass
     assert stack.K == 1
     L, Fd = stack.L, stack.F
     p = p.contiguous().float()

@@ -77,3 +77,39 @@ def test_seeded_construction_reproduces_reference_weights():
         sys.path.remove('/root/reference')
         for m in [m for m in sys.modules if m == 'lib' or m.startswith('lib.')]:
             del sys.modules[m]
+
+
+def test_flat_storage_survives_syncbn_conversion_and_zero_grad():
+    """The decoder tensors live in flat masters (views keep the module API).  Converting to
+    SyncBatchNorm AFTER the stack exists (train_ae.py:152 does it right before DDP), moving values
+    with load_state_dict, and zero_grad(set_to_none=True) must all keep masters and modules in sync."""
+    gd = Golden('small_free_learned')
+    model = build_dropin(gd)
+    stack = model.flow_stack()
+    stack.prepare()
+    ref = {k: v.clone() for k, v in model.state_dict().items()}
+    model = torch.nn.SyncBatchNorm.convert_sync_batchnorm(model)
+    stack.prepare()
+    assert stack._is_flat()
+    for k, v in model.state_dict().items():
+        assert torch.equal(v, ref[k]), k
+    # masters and module tensors are the same memory
+    key = 'pc_decoder.1.flows.1.nvp3.T_logvar_0.logvar_sd1_bn.running_var'
+    stack.masters['bn'].tensor.mul_(2.0)
+    assert torch.allclose(model.state_dict()[key], 2.0 * ref[key])
+    model.load_state_dict(ref, strict=True)
+    assert stack._is_flat()
+    assert torch.allclose(model.state_dict()[key], ref[key])
+    # gradients: autograd on the masters, .grad views on the parameters, reset by zero_grad
+    g = gd.t('in/g', torch.float32)
+    model.eval()
+    stack.film(g, False, False).sum().backward()
+    w = model.pc_decoder[2].flows[0].nvp2.T_mu_0_cond_b[3].weight
+    g1 = w.grad.clone()
+    assert float(g1.abs().sum()) > 0
+    model.zero_grad(set_to_none=True)
+    stack.prepare()
+    stack.film(g, False, False).sum().backward()
+    assert torch.allclose(w.grad, g1)            # not accumulated on top of the stale master gradient
+    stack.film(g, False, False).sum().backward()
+    assert torch.allclose(w.grad, 2 * g1)        # but accumulated across backward calls like autograd does
