@@ -8,6 +8,7 @@
 #include "gwtf_common.cuh"
 #include "gwtf_fwd.cuh"
 #include "gwtf_tc_fwd.cuh"
+#include "gwtf_tc_persist.cuh"
 #include "gwtf_bwd.cuh"
 #include "gwtf_sample.cuh"
 
@@ -44,15 +45,17 @@ int check_desc(const gwtf_stack_desc* d) {
     return 0;
 }
 
-int g_use_tc = -1;    // -1: decide from the environment (GWTF_TC, default on), 0 / 1: forced
+int g_use_tc = -1;    // -1: decide from the environment (GWTF_TC), 0 = FMA, 1 = tcgen05 (3 CTAs/SM),
+                      // 2 = tcgen05 persistent warp-specialised (1 CTA/SM, 4 tiles in flight)
 
-bool use_tc(int F) {
+int tc_mode(int F) {
     if (g_use_tc < 0) {
         const char* e = getenv("GWTF_TC");
-        g_use_tc = (e && e[0] == '0') ? 0 : 1;
+        g_use_tc = e ? (e[0] == '0' ? 0 : (e[0] == '1' ? 1 : 2)) : 2;
     }
-    return g_use_tc == 1 && F <= 39;    // tensor-memory tile budget: F + 1 (bias channel) <= 40; configs use 33 / 37
+    return F <= 39 ? g_use_tc : 0;      // tensor-memory tile budget: F + 1 (bias channel) <= 40; configs use 33 / 37
 }
+bool use_tc(int F) { return tc_mode(F) != 0; }
 
 int padded_features(int F) {
     const int opts[] = {8, 16, 24, 32, 36, 40, 48, 64};
@@ -159,6 +162,23 @@ int launch_fwd_layer_tc(const LayerArgs& a0, cudaStream_t st) {
     return 0;
 }
 
+template <int FPK, int FPN, int PHASE>
+int launch_fwd_layer_tcp(const LayerArgs& a0, cudaStream_t st) {
+    LayerArgs a = a0;
+    a.tiles_per_shape = (a.N + 127) / 128;
+    const int F = a.d.n_features, K = a.d.n_components;
+    const size_t smem = round_up((int)sizeof(TcPersistSmem<FPK, FPN>), 16) + (size_t)round_up(raw_floats(F), 4) * 4;
+    auto kern = k_fwd_layer_tcp<FPK, FPN, PHASE>;
+    GWTF_CUDA(allow_smem(kern, smem));
+    const int tiles = a.B * a.tiles_per_shape;
+    int gx = num_sms() / K;                                  // one CTA per SM owns all 512 TMEM columns
+    if (gx > (tiles + kSlots - 1) / kSlots) gx = (tiles + kSlots - 1) / kSlots;
+    if (gx < 1) gx = 1;
+    kern<<<dim3(gx, K), kPersistThreads, smem, st>>>(a);
+    GWTF_CUDA(cudaGetLastError());
+    return 0;
+}
+
 template <int FP, int PHASE>
 int launch_fwd_layer(const LayerArgs& a0, cudaStream_t st) {
     constexpr int P = PointsPerThread<FP>::fwd;
@@ -186,7 +206,7 @@ int gwtf_version(void) { return 1; }
 
 int gwtf_set_tensor_cores(int32_t enable) {
     const int prev = g_use_tc;
-    g_use_tc = enable < 0 ? -1 : (enable ? 1 : 0);
+    g_use_tc = enable < 0 ? -1 : (enable > 2 ? 2 : enable);
     return prev;
 }
 const char* gwtf_last_error_string(void) { return g_err; }
@@ -246,6 +266,11 @@ int gwtf_fwd_layer_ex(const gwtf_stack_desc* desc, int32_t layer, int32_t phase,
     a.d = *desc; a.layer = layer; a.train = train; a.direct = direct; a.params = params; a.bnbuf = bnbuf; a.film = film;
     a.xin = xin; a.xin_shared = xin_shared; a.xout = xout; a.ld = ld; a.ssum = ssum; a.trio = trio; a.y1out = y1out;
     a.mom_in = mom_in; a.mom_out = mom_out; a.sum1 = sum1; a.B = B; a.N = N; a.n_total = n_total; a.tiles_per_shape = 0;
+    if (tc_mode(desc->n_features) == 2 && desc->n_components <= num_sms()) {
+        if (phase == 0) { GWTF_DISPATCH_TC(desc->n_features, return (launch_fwd_layer_tcp<FPK, FPN, 0>(a, (cudaStream_t)stream))); }
+        else { GWTF_DISPATCH_TC(desc->n_features, return (launch_fwd_layer_tcp<FPK, FPN, 1>(a, (cudaStream_t)stream))); }
+        return 0;
+    }
     if (use_tc(desc->n_features)) {
         if (phase == 0) { GWTF_DISPATCH_TC(desc->n_features, return (launch_fwd_layer_tc<FPK, FPN, 0>(a, (cudaStream_t)stream))); }
         else { GWTF_DISPATCH_TC(desc->n_features, return (launch_fwd_layer_tc<FPK, FPN, 1>(a, (cudaStream_t)stream))); }

@@ -57,8 +57,9 @@ typedef struct gwtf_stack_desc {
 } gwtf_stack_desc;
 
 int gwtf_version(void);
-/* Contraction engine of the per-layer kernels: 1 = tcgen05 tensor cores (3xTF32, TMEM accumulators;
- * default, feature widths <= 40), 0 = FP32 FMA pipe, -1 = re-read the GWTF_TC environment variable.
+/* Contraction engine of the per-layer forward kernels: 2 = tcgen05 tensor cores, persistent
+ * warp-specialised kernel (default; 3xTF32, TMEM accumulators, feature widths <= 39), 1 = tcgen05
+ * with one tile per 128-thread CTA, 0 = FP32 FMA pipe, -1 = re-read the GWTF_TC environment variable.
  * Returns the previous setting (NOT an error code). */
 int gwtf_set_tensor_cores(int32_t enable);
 const char* gwtf_last_error_string(void);
