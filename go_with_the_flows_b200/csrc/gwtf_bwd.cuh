@@ -332,6 +332,19 @@ __global__ void __launch_bounds__(kThreads) k_bwd_layer_d(const BwdArgs a) {
     if (cur_b >= 0) flush(cur_b);
 }
 
+// warp-level tensor-core MMA (register fragments) for the weight-gradient GEMM of phase 1:
+// D(16x8) += A(16x8, row) * B(8x8, col), tf32 inputs, fp32 accumulate.  fp32-grade accuracy from the
+// 3xTF32 split of both operands.
+__device__ __forceinline__ void mma_m16n8k8_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+__device__ __forceinline__ void split_tf32_bits(float x, uint32_t& hi, uint32_t& lo) {
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
+    lo = __float_as_uint(x - __uint_as_float(hi));
+}
+
 // ---- PHASE 1: sd1 / sd0 / bn0 gradients and the input gradient --------------------------------
 template <int FP>
 struct BwdESmem {
@@ -356,12 +369,12 @@ __global__ void __launch_bounds__(kThreads) k_bwd_layer_e(const BwdArgs a) {
     constexpr int EG = 4;                                   // e's per reduce-scatter group (5 sums each); 4 so
                                                             // that a0 is written as one conflict-free STS.128
     constexpr int NGE = (FP + EG - 1) / EG;
-    // GEMM ownership: 8x8 blocks of dW1[f][e], NQ point groups
-    constexpr int FB = (FP + 7) / 8;
-    constexpr int NBLK = FB * FB;
-    constexpr int NQ = kThreads / NBLK >= 8 ? 8 : (kThreads / NBLK >= 4 ? 4 : (kThreads / NBLK >= 2 ? 2 : 1));
-    static_assert(NBLK * NQ <= kThreads, "GEMM thread mapping");
+    // weight-gradient GEMM dW1[f][e] = sum_rows Dh[row][f] * A0s[row][e] on the tensor cores (mma.sync
+    // m16n8k8 tf32, 3xTF32): each warp owns 1/8 of the tile's rows and the whole (MT*16) x (NT*8) output
+    constexpr int MT = (FP + 15) / 16, NT = (FP + 7) / 8;
+    constexpr int NWARPS = kThreads / 32;
     constexpr int ROWS = P * kThreads;
+    static_assert(ROWS % (NWARPS * 8) == 0, "rows per warp must be a multiple of the MMA K");
 
     LayerSrc src;
     src.params = a.params + (size_t)(j * L + l) * a.d.rec_stride;
@@ -387,18 +400,18 @@ __global__ void __launch_bounds__(kThreads) k_bwd_layer_e(const BwdArgs a) {
     float* dpr = a.dparams + (size_t)(j * L + l) * a.d.rec_stride;
     double* bs = a.bsum + (size_t)j * 8 * F;
 
-    const int blk = tid % NBLK, q = tid / NBLK;
-    const int fb = blk / FB, eb = blk - fb * FB;
-    const bool gemm_thread = q < NQ;
+    const int warp = tid >> 5, fg = lane >> 2, ft = lane & 3;      // MMA fragment coordinates
     const int total_tiles = B * a.tiles_per_shape;
 
 #pragma unroll 1
     for (int net = 0; net < 2; ++net) {
-        float gacc[8][8];
+        float gacc[MT][NT][4];
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
+        for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-            for (int jj = 0; jj < 8; ++jj) gacc[i][jj] = 0.f;
+            for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) gacc[mt][nt][i] = 0.f;
         float eacc[NGE];
 #pragma unroll
         for (int g = 0; g < NGE; ++g) eacc[g] = 0.f;
@@ -520,26 +533,35 @@ __global__ void __launch_bounds__(kThreads) k_bwd_layer_e(const BwdArgs a) {
                     for (int d = 0; d < 3; ++d) a.gbuf[sb + (size_t)d * N + n] += vin[p][d];
             }
             __syncthreads();
-            // dW1[f][e] += sum_rows Dh[row][f] * A0s[row][e]
-            if (gemm_thread) {
-                const int r0 = q * (ROWS / NQ), r1 = r0 + ROWS / NQ;
-                const float4* dh4 = reinterpret_cast<const float4*>(Dh);
-                const float4* a04 = reinterpret_cast<const float4*>(A0s);
-#pragma unroll 2
-                for (int r = r0; r < r1; ++r) {
-                    float df[8], ae[8];
+            // dW1[f][e] += sum_rows Dh[row][f] * A0s[row][e]   (A = Dh^T: m = f, k = row; B: k = row, n = e)
+            {
+                const int r0 = warp * (ROWS / NWARPS);
+#pragma unroll 1
+                for (int kk = 0; kk < ROWS / NWARPS; kk += 8) {
+                    const float* dr0 = Dh + (size_t)(r0 + kk + ft) * FP;
+                    const float* dr1 = dr0 + 4 * FP;
+                    const float* ar0 = A0s + (size_t)(r0 + kk + ft) * FP;
+                    const float* ar1 = ar0 + 4 * FP;
+                    uint32_t bh[NT][2], bl[NT][2];
 #pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const bool okf = (fb * 8 + h * 4) < FP, oke = (eb * 8 + h * 4) < FP;
-                        const float4 d4 = okf ? dh4[(size_t)r * (FP / 4) + fb * 2 + h] : make_float4(0.f, 0.f, 0.f, 0.f);
-                        const float4 a4 = oke ? a04[(size_t)r * (FP / 4) + eb * 2 + h] : make_float4(0.f, 0.f, 0.f, 0.f);
-                        df[h * 4 + 0] = d4.x; df[h * 4 + 1] = d4.y; df[h * 4 + 2] = d4.z; df[h * 4 + 3] = d4.w;
-                        ae[h * 4 + 0] = a4.x; ae[h * 4 + 1] = a4.y; ae[h * 4 + 2] = a4.z; ae[h * 4 + 3] = a4.w;
+                    for (int nt = 0; nt < NT; ++nt) {
+                        split_tf32_bits(ar0[nt * 8 + fg], bh[nt][0], bl[nt][0]);
+                        split_tf32_bits(ar1[nt * 8 + fg], bh[nt][1], bl[nt][1]);
                     }
 #pragma unroll
-                    for (int i = 0; i < 8; ++i)
+                    for (int mt = 0; mt < MT; ++mt) {
+                        uint32_t ah[4], al[4];
+                        split_tf32_bits(dr0[mt * 16 + fg], ah[0], al[0]);
+                        split_tf32_bits(dr0[mt * 16 + fg + 8], ah[1], al[1]);
+                        split_tf32_bits(dr1[mt * 16 + fg], ah[2], al[2]);
+                        split_tf32_bits(dr1[mt * 16 + fg + 8], ah[3], al[3]);
 #pragma unroll
-                        for (int jj = 0; jj < 8; ++jj) gacc[i][jj] = fmaf(df[i], ae[jj], gacc[i][jj]);
+                        for (int nt = 0; nt < NT; ++nt) {
+                            mma_m16n8k8_tf32(gacc[mt][nt], ah, bh[nt]);
+                            mma_m16n8k8_tf32(gacc[mt][nt], al, bh[nt]);
+                            mma_m16n8k8_tf32(gacc[mt][nt], ah, bl[nt]);
+                        }
+                    }
                 }
             }
             __syncthreads();
@@ -566,24 +588,32 @@ __global__ void __launch_bounds__(kThreads) k_bwd_layer_e(const BwdArgs a) {
                 if (col >= 0) atomicAdd(&dpr[net * o.stride + o.W0 + e * k + col], val);
             }
         }
-        // ---- flush dW1: reduce the NQ partial blocks through shared memory (reuses Dh)
-        __syncthreads();
-        float* part = Dh;                                   // [NQ][FB*8][FB*8]
-        constexpr int FP8 = FB * 8;
-        if (gemm_thread) {
+        // ---- flush dW1: reduce the per-warp partial outputs through shared memory (reuses Dh/A0s),
+        // four warps at a time so the staging buffer stays within the operand area for every width
+        constexpr int PM = MT * 16, PN = NT * 8;
+        float* part = Dh;                                   // [4][MT*16][NT*8]
+#pragma unroll 1
+        for (int half = 0; half < NWARPS / 4; ++half) {
+            __syncthreads();
+            if ((warp >> 2) == half) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
+                for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-                for (int jj = 0; jj < 8; ++jj)
-                    part[((size_t)q * FP8 + fb * 8 + i) * FP8 + eb * 8 + jj] = gacc[i][jj];
-        }
-        __syncthreads();
-        for (int i = tid; i < F * F; i += kThreads) {
-            const int f = i / F, e = i - f * F;
-            float s = 0.f;
+                    for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
-            for (int qq = 0; qq < NQ; ++qq) s += part[((size_t)qq * FP8 + f) * FP8 + e];
-            atomicAdd(&dpr[net * o.stride + o.W1 + f * F + e], s);
+                        for (int i = 0; i < 4; ++i) {
+                            const int f = mt * 16 + fg + ((i & 2) ? 8 : 0), e = nt * 8 + 2 * ft + (i & 1);
+                            part[((size_t)(warp & 3) * PM + f) * PN + e] = gacc[mt][nt][i];
+                        }
+            }
+            __syncthreads();
+            for (int i = tid; i < F * F; i += kThreads) {
+                const int f = i / F, e = i - f * F;
+                float s = 0.f;
+#pragma unroll
+                for (int qq = 0; qq < 4; ++qq) s += part[((size_t)qq * PM + f) * PN + e];
+                atomicAdd(&dpr[net * o.stride + o.W1 + f * F + e], s);
+            }
         }
         __syncthreads();
     }
