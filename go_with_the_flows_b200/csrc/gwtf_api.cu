@@ -10,6 +10,7 @@
 #include "gwtf_tc_fwd.cuh"
 #include "gwtf_tc_persist.cuh"
 #include "gwtf_bwd.cuh"
+#include "gwtf_bwd_mma.cuh"
 #include "gwtf_sample.cuh"
 
 using namespace gwtf;
@@ -56,6 +57,13 @@ int tc_mode(int F) {
     return F <= 39 ? g_use_tc : 0;      // tensor-memory tile budget: F + 1 (bias channel) <= 40; configs use 33 / 37
 }
 bool use_tc(int F) { return tc_mode(F) != 0; }
+// backward contractions on mma.sync register fragments (any F <= 64) unless the FMA engine is selected;
+// GWTF_MMA_BWD=0 keeps the CUDA-core backward for A/B timing
+bool use_mma_bwd() {
+    static int env = -1;
+    if (env < 0) { const char* e = getenv("GWTF_MMA_BWD"); env = (e && e[0] == '0') ? 0 : 1; }
+    return tc_mode(1) != 0 && env != 0;
+}
 
 int padded_features(int F) {
     const int opts[] = {8, 16, 24, 32, 36, 40, 48, 64};

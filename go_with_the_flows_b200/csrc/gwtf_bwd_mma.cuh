@@ -1,0 +1,388 @@
+// Backward phase 1 (sd1 / sd0 / bn0 gradients + input gradient) with every contraction on the tensor
+// cores through warp-level register fragments (mma.sync.m16n8k8 tf32, 3xTF32 split = fp32-grade).
+//
+// Replaces the CUDA-core contractions of k_bwd_layer_e (gwtf_bwd.cuh); same BwdArgs, same outputs.
+// Reference semantics: lib/networks/flow.py (CondRealNVPFlow3D.forward, autograd of the F->F block).
+//
+// One warp owns tiles of 16 points (the MMA M dimension) and runs the whole chain on them without any
+// CTA-level synchronisation:
+//   a0  = relu(q0 x)                       computed straight into the A-fragment layout
+//   h1  = a0 W1^T                          MMA #1  (B fragments pre-split hi/lo in shared memory)
+//   dh1 = g(h1, dO)                        element-wise on the C fragments
+//   da0 = dh1 W1                           MMA #2  (C fragment -> A fragment is free: the k index of a
+//                                          contraction may be permuted, so B is staged with k = 2t, 2t+1)
+//   dy0 = da0 * [y0 > 0]  -> per-channel sums (registers, reduced once per CTA) and the input gradient
+//   dW1 += dh1^T a0                        MMA #3  (k = points: the two tiles take a trip through the
+//                                          warp's private shared-memory tile to transpose)
+#pragma once
+#include "gwtf_bwd.cuh"
+
+namespace gwtf {
+
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// row stride of the per-warp transpose tiles: == 8 (mod 16) makes the k-major fragment loads of MMA #3
+// and the float2 stores of the C fragments conflict-free
+__host__ __device__ constexpr int mma_tile_stride(int FP) { return (FP % 16 == 8) ? FP : FP + 8; }
+
+template <int FP>
+struct BwdEMmaSmem {
+    LayerW<FP> W;
+    LayerWB<FP> WB;
+    uint64_t bar;
+    float4 cf1[FP];         // current (net, shape): (st.x, st.y, A1, A0)   dh1 = [y1>0] w2s.dO + h*A1 + A0
+    float4 cf2[FP];         //                       w2s = sd2 columns * s * istd1
+    float red[round_up(5 * FP, 32)];
+};
+
+template <int FP>
+__host__ __device__ constexpr size_t bwd_e_mma_smem(int F) {
+    return round_up((int)sizeof(BwdEMmaSmem<FP>), 16) + (size_t)round_up(raw_floats(F), 4) * 4 +
+           2 * (size_t)(FP / 8) * (FP / 8) * 32 * 16 +                       // B fragments of MMA #1, #2 (one net)
+           (size_t)(kThreads / 32) * 2 * 16 * mma_tile_stride(FP) * 4;       // per-warp dh1 / a0 tiles
+}
+
+template <int FP>
+__global__ void __launch_bounds__(kThreads, 1) k_bwd_layer_e_mma(const BwdArgs a) {
+    static_assert(FP % 8 == 0, "feature width padded to the MMA K");
+    constexpr int KS = FP / 8, NT = FP / 8, MT = (FP + 15) / 16;
+    constexpr int FPS = mma_tile_stride(FP);
+    constexpr int NW = kThreads / 32;
+    constexpr int TILE = NW * 16;                            // points per CTA tile
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    BwdEMmaSmem<FP>& S = *reinterpret_cast<BwdEMmaSmem<FP>*>(smem_raw);
+    float* raw = reinterpret_cast<float*>(smem_raw + round_up((int)sizeof(BwdEMmaSmem<FP>), 16));
+    const int F = a.d.n_features, K = a.d.n_components, L = a.d.n_layers;
+    float4* bf1 = reinterpret_cast<float4*>(raw + round_up(raw_floats(F), 4));    // [KS][NT][32]
+    float4* bf2 = bf1 + KS * NT * 32;
+    float* tiles = reinterpret_cast<float*>(bf2 + KS * NT * 32);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    float* Dw = tiles + (size_t)warp * 2 * 16 * FPS;         // [16][FPS] dh1 of the warp's tile
+    float* Aw = Dw + 16 * FPS;                               // [16][FPS] a0
+    const int j = blockIdx.y, l = a.layer;
+    const int N = a.N, B = a.B;
+    const bool train = a.train != 0;
+
+    LayerSrc src;
+    src.params = a.params + (size_t)(j * L + l) * a.d.rec_stride;
+    src.bn = a.bnbuf + (size_t)(j * L + l) * 8 * F;
+    src.film = nullptr;
+    src.mom = a.mom_in ? a.mom_in + j * GWTF_MOM_STRIDE : nullptr;
+    src.sum1 = a.sum1 ? a.sum1 + (size_t)j * 4 * F : nullptr;
+    src.n_total = a.n_total;
+
+    if (tid == 0) { mbar_init(&S.bar, 1); mbar_fence_init(); }
+    __syncthreads();
+    if (tid == 0) issue_layer_copy(raw, src, F, !train, false, &S.bar);
+    mbar_wait(&S.bar, 0u);
+    stage_layer<FP, true>(S.W, &S.WB, raw, src, F, a.d.warp_mask[l], train, false,
+                          train ? a.bsum + (size_t)j * 8 * F : nullptr, tid, kThreads);
+
+    const unsigned wm = a.d.warp_mask[l];
+    const int w = popc3(wm), k = 3 - w;
+    const NetOffsets o = net_offsets(F, w);
+    int col_of_dim[3];
+    { int q = 0; for (int dd = 0; dd < 3; ++dd) col_of_dim[dd] = (wm & (1u << dd)) ? -1 : q++; }
+    float* dpr = a.dparams + (size_t)(j * L + l) * a.d.rec_stride;
+    double* bs = a.bsum + (size_t)j * 8 * F;
+
+    const int tps = (N + TILE - 1) / TILE;
+    const long long total_tiles = (long long)B * tps;
+    const int t_begin = (int)(total_tiles * blockIdx.x / gridDim.x);
+    const int t_end = (int)(total_tiles * (blockIdx.x + 1) / gridDim.x);
+
+#pragma unroll 1
+    for (int net = 0; net < 2; ++net) {
+        __syncthreads();                                     // W ready / previous net done with bf*, tiles
+        // ---- B fragments of this net, pre-split: (b0.hi, b1.hi, b0.lo, b1.lo) per lane
+        for (int i = tid; i < KS * NT * 32; i += kThreads) {
+            const int ln = i & 31, nt = (i >> 5) % NT, ks = (i >> 5) / NT;
+            const int gg = ln >> 2, tt = ln & 3;
+            uint32_t h0, l0, h1, l1;
+            // MMA #1: k = e (A columns t, t+4 <-> e = 8ks+2t, 8ks+2t+1), n = f = 8nt+g
+            split_tf32_bits(S.W.W1T[net][8 * ks + 2 * tt][8 * nt + gg], h0, l0);
+            split_tf32_bits(S.W.W1T[net][8 * ks + 2 * tt + 1][8 * nt + gg], h1, l1);
+            bf1[i] = make_float4(__uint_as_float(h0), __uint_as_float(h1), __uint_as_float(l0), __uint_as_float(l1));
+            // MMA #2: k = f (8ks+2t, 8ks+2t+1), n = e = 8nt+g
+            split_tf32_bits(S.W.W1T[net][8 * nt + gg][8 * ks + 2 * tt], h0, l0);
+            split_tf32_bits(S.W.W1T[net][8 * nt + gg][8 * ks + 2 * tt + 1], h1, l1);
+            bf2[i] = make_float4(__uint_as_float(h0), __uint_as_float(h1), __uint_as_float(l0), __uint_as_float(l1));
+        }
+        float gacc[MT][NT][4];
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) gacc[mt][nt][i] = 0.f;
+        float es[NT][2][5];                                   // per-e sums of this lane's rows: e = 8nt+2t+i
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int c = 0; c < 5; ++c) es[nt][i][c] = 0.f;
+
+        int cur_b = -1;
+#pragma unroll 1
+        for (int tile = t_begin; tile < t_end; ++tile) {
+            const int b = tile / tps;
+            const int n0 = (tile - b * tps) * TILE + warp * 16;
+            if (b != cur_b) {
+                __syncthreads();
+                if (tid < FP) {
+                    const int f = tid;
+                    float4 c1 = make_float4(0.f, 0.f, 0.f, 0.f), c2 = c1;
+                    if (f < F) {
+                        const float* film = a.film + ((size_t)(b * K + j) * L + l) * 4 * F;
+                        const float s = film[net * 2 * F + f], tt = film[net * 2 * F + F + f];
+                        const float2 mi = S.W.mi1[net][f];
+                        const float2 ab = S.WB.ab1[net][f];
+                        const float4 w2 = S.W.w2[net][f];
+                        const float sc = s * mi.y;
+                        c1 = make_float4(sc, tt - s * mi.x, -mi.y * mi.y * ab.y, mi.y * (mi.x * ab.y - ab.x));
+                        c2 = make_float4(w2.x * sc, w2.y * sc, w2.z * sc, 0.f);
+                    }
+                    S.cf1[f] = c1;
+                    S.cf2[f] = c2;
+                }
+                __syncthreads();
+                cur_b = b;
+            }
+            // ---- this lane's two rows (points) of the tile
+            const float* xin = a.xin_shared ? a.xin + (size_t)b * 3 * N : a.xin + ((size_t)j * B + b) * 3 * N;
+            const size_t sb = ((size_t)j * B + b) * 3 * N;
+            const float* dob = a.dobuf + ((size_t)j * B + b) * 6 * N + (size_t)net * 3 * N;
+            float x[2][3], dO[2][3], gold[2];
+            bool valid[2];
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const int n = n0 + g + 8 * r;
+                valid[r] = n < N;
+#pragma unroll
+                for (int d = 0; d < 3; ++d) {
+                    x[r][d] = valid[r] ? xin[(size_t)d * N + n] : 0.f;
+                    dO[r][d] = valid[r] ? dob[(size_t)d * N + n] : 0.f;
+                }
+                gold[r] = (valid[r] && t < 3) ? a.gbuf[sb + (size_t)t * N + n] : 0.f;
+            }
+            // ---- a0 (A fragments) and MMA #1: h1[row][f]
+            float h[NT][4];
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) h[nt][0] = h[nt][1] = h[nt][2] = h[nt][3] = 0.f;
+            uint32_t mask0 = 0u, mask1 = 0u;                  // [y0 > 0] of rows g, g+8; bit = 2ks+i
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks) {
+                const float4 qa = S.W.q0[net][8 * ks + 2 * t];
+                const float4 qb = S.W.q0[net][8 * ks + 2 * t + 1];
+                float av[4];
+                av[0] = fmaf(qa.x, x[0][0], fmaf(qa.y, x[0][1], fmaf(qa.z, x[0][2], qa.w)));   // (row g,   e0)
+                av[1] = fmaf(qa.x, x[1][0], fmaf(qa.y, x[1][1], fmaf(qa.z, x[1][2], qa.w)));   // (row g+8, e0)
+                av[2] = fmaf(qb.x, x[0][0], fmaf(qb.y, x[0][1], fmaf(qb.z, x[0][2], qb.w)));   // (row g,   e1)
+                av[3] = fmaf(qb.x, x[1][0], fmaf(qb.y, x[1][1], fmaf(qb.z, x[1][2], qb.w)));   // (row g+8, e1)
+                mask0 |= (av[0] > 0.f ? 1u : 0u) << (2 * ks) | (av[2] > 0.f ? 2u : 0u) << (2 * ks);
+                mask1 |= (av[1] > 0.f ? 1u : 0u) << (2 * ks) | (av[3] > 0.f ? 2u : 0u) << (2 * ks);
+                av[0] = valid[0] ? fmaxf(av[0], 0.f) : 0.f;
+                av[2] = valid[0] ? fmaxf(av[2], 0.f) : 0.f;
+                av[1] = valid[1] ? fmaxf(av[1], 0.f) : 0.f;
+                av[3] = valid[1] ? fmaxf(av[3], 0.f) : 0.f;
+                *reinterpret_cast<float2*>(Aw + g * FPS + 8 * ks + 2 * t) = make_float2(av[0], av[2]);
+                *reinterpret_cast<float2*>(Aw + (g + 8) * FPS + 8 * ks + 2 * t) = make_float2(av[1], av[3]);
+                uint32_t ah[4], al[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) split_tf32_bits(av[i], ah[i], al[i]);
+                float4 bq[NT];
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) bq[nt] = bf1[(ks * NT + nt) * 32 + lane];
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) mma_tf32(h[nt], ah, __float_as_uint(bq[nt].x), __float_as_uint(bq[nt].y));
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) mma_tf32(h[nt], al, __float_as_uint(bq[nt].x), __float_as_uint(bq[nt].y));
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) mma_tf32(h[nt], ah, __float_as_uint(bq[nt].z), __float_as_uint(bq[nt].w));
+            }
+            // ---- h1 -> dh1 on the C fragments: h[nt][2r+i] = (row g+8r, f = 8nt+2t+i)
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) {
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const float4 c1 = S.cf1[8 * nt + 2 * t + i];
+                    const float4 c2 = S.cf2[8 * nt + 2 * t + i];
+#pragma unroll
+                    for (int r = 0; r < 2; ++r) {
+                        const float hv = h[nt][2 * r + i];
+                        const float y1 = fmaf(c1.x, hv, c1.y);
+                        const float da = fmaf(c2.x, dO[r][0], fmaf(c2.y, dO[r][1], c2.z * dO[r][2]));
+                        const float dh = (y1 > 0.f ? da : 0.f) + fmaf(hv, c1.z, c1.w);
+                        h[nt][2 * r + i] = valid[r] ? dh : 0.f;
+                    }
+                }
+                *reinterpret_cast<float2*>(Dw + g * FPS + 8 * nt + 2 * t) = make_float2(h[nt][0], h[nt][1]);
+                *reinterpret_cast<float2*>(Dw + (g + 8) * FPS + 8 * nt + 2 * t) = make_float2(h[nt][2], h[nt][3]);
+            }
+            // ---- MMA #2: da0[row][e] = sum_f dh1[row][f] W1[f][e]
+            float da0[NT][4];
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) da0[nt][0] = da0[nt][1] = da0[nt][2] = da0[nt][3] = 0.f;
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks) {
+                uint32_t ah[4], al[4];
+                split_tf32_bits(h[ks][0], ah[0], al[0]);      // (row g,   f = 8ks+2t)
+                split_tf32_bits(h[ks][2], ah[1], al[1]);      // (row g+8, f = 8ks+2t)
+                split_tf32_bits(h[ks][1], ah[2], al[2]);      // (row g,   f = 8ks+2t+1)
+                split_tf32_bits(h[ks][3], ah[3], al[3]);      // (row g+8, f = 8ks+2t+1)
+                float4 bq[NT];
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) bq[nt] = bf2[(ks * NT + nt) * 32 + lane];
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) mma_tf32(da0[nt], ah, __float_as_uint(bq[nt].x), __float_as_uint(bq[nt].y));
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) mma_tf32(da0[nt], al, __float_as_uint(bq[nt].x), __float_as_uint(bq[nt].y));
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) mma_tf32(da0[nt], ah, __float_as_uint(bq[nt].z), __float_as_uint(bq[nt].w));
+            }
+            // ---- relu/bn0/sd0 pieces: da0[nt][2r+i] = (row g+8r, e = 8nt+2t+i)
+            float vin[2][3];
+#pragma unroll
+            for (int r = 0; r < 2; ++r) vin[r][0] = vin[r][1] = vin[r][2] = 0.f;
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) {
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const float4 qv = S.W.q0[net][8 * nt + 2 * t + i];
+                    const float4 rv = S.WB.r0[net][8 * nt + 2 * t + i];
+#pragma unroll
+                    for (int r = 0; r < 2; ++r) {
+                        const uint32_t m = r == 0 ? mask0 : mask1;
+                        const float dy0 = ((m >> (2 * nt + i)) & 1u) ? da0[nt][2 * r + i] : 0.f;
+                        const float hh = fmaf(rv.x, x[r][0], fmaf(rv.y, x[r][1], fmaf(rv.z, x[r][2], rv.w)));
+                        vin[r][0] = fmaf(qv.x, dy0, vin[r][0]);
+                        vin[r][1] = fmaf(qv.y, dy0, vin[r][1]);
+                        vin[r][2] = fmaf(qv.z, dy0, vin[r][2]);
+                        es[nt][i][0] = fmaf(dy0, hh, es[nt][i][0]);          // d gamma0
+                        es[nt][i][1] += dy0;                                 // d beta0
+                        es[nt][i][2] = fmaf(dy0, x[r][0], es[nt][i][2]);     // raw sd0 weight sums
+                        es[nt][i][3] = fmaf(dy0, x[r][1], es[nt][i][3]);
+                        es[nt][i][4] = fmaf(dy0, x[r][2], es[nt][i][4]);
+                    }
+                }
+            }
+            // input gradient: sum over the 4 lanes that share a row, lane t < 3 writes dimension t
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+#pragma unroll
+                for (int d = 0; d < 3; ++d) {
+                    vin[r][d] += __shfl_xor_sync(0xffffffffu, vin[r][d], 1);
+                    vin[r][d] += __shfl_xor_sync(0xffffffffu, vin[r][d], 2);
+                }
+                const float v = t == 0 ? vin[r][0] : (t == 1 ? vin[r][1] : vin[r][2]);
+                const int n = n0 + g + 8 * r;
+                if (valid[r] && t < 3) a.gbuf[sb + (size_t)t * N + n] = gold[r] + v;
+            }
+            __syncwarp();
+            // ---- MMA #3: dW1[f][e] += sum_rows dh1[row][f] a0[row][e]   (m = f, n = e, k = row)
+#pragma unroll
+            for (int kk = 0; kk < 16; kk += 8) {
+                const float* dr0 = Dw + (kk + t) * FPS;
+                const float* dr1 = dr0 + 4 * FPS;
+                const float* ar0 = Aw + (kk + t) * FPS;
+                const float* ar1 = ar0 + 4 * FPS;
+                uint32_t bh[NT][2], bl[NT][2];
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) {
+                    split_tf32_bits(ar0[nt * 8 + g], bh[nt][0], bl[nt][0]);
+                    split_tf32_bits(ar1[nt * 8 + g], bh[nt][1], bl[nt][1]);
+                }
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt) {
+                    constexpr bool kHalfLast = (FP % 16) != 0;   // last m-tile has only 8 real rows
+                    const bool upper = !(kHalfLast && mt == MT - 1);
+                    uint32_t ah[4], al[4];
+                    split_tf32_bits(dr0[mt * 16 + g], ah[0], al[0]);
+                    split_tf32_bits(dr1[mt * 16 + g], ah[2], al[2]);
+                    if (upper) {
+                        split_tf32_bits(dr0[mt * 16 + g + 8], ah[1], al[1]);
+                        split_tf32_bits(dr1[mt * 16 + g + 8], ah[3], al[3]);
+                    } else {
+                        ah[1] = al[1] = ah[3] = al[3] = 0u;
+                    }
+#pragma unroll
+                    for (int nt = 0; nt < NT; ++nt) mma_tf32(gacc[mt][nt], ah, bh[nt][0], bh[nt][1]);
+#pragma unroll
+                    for (int nt = 0; nt < NT; ++nt) mma_tf32(gacc[mt][nt], al, bh[nt][0], bh[nt][1]);
+#pragma unroll
+                    for (int nt = 0; nt < NT; ++nt) mma_tf32(gacc[mt][nt], ah, bl[nt][0], bl[nt][1]);
+                }
+            }
+            __syncwarp();
+        }
+
+        // ---- flush the per-e sums of this net: lanes with the same t hold the same channels
+        __syncthreads();
+        for (int i = tid; i < round_up(5 * FP, 32); i += kThreads) S.red[i] = 0.f;
+        __syncthreads();
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int c = 0; c < 5; ++c) {
+                    float v = es[nt][i][c];
+                    v += __shfl_xor_sync(0xffffffffu, v, 4);
+                    v += __shfl_xor_sync(0xffffffffu, v, 8);
+                    v += __shfl_xor_sync(0xffffffffu, v, 16);
+                    if (g == 0) atomicAdd(&S.red[(8 * nt + 2 * t + i) * 5 + c], v);
+                }
+        __syncthreads();
+        for (int i = tid; i < 5 * FP; i += kThreads) {
+            const int e = i / 5, c = i - 5 * e;
+            if (e >= F) continue;
+            const float val = S.red[i];
+            if (c == 0) {
+                atomicAdd(&dpr[net * o.stride + o.g0 + e], val);
+                atomicAdd(&bs[(net * 4 + 3) * F + e], (double)val);
+            } else if (c == 1) {
+                atomicAdd(&dpr[net * o.stride + o.b0 + e], val);
+                atomicAdd(&bs[(net * 4 + 2) * F + e], (double)val);
+            } else {
+                const int col = col_of_dim[c - 2];
+                if (col >= 0) atomicAdd(&dpr[net * o.stride + o.W0 + e * k + col], val);
+            }
+        }
+        // ---- flush dW1: per-warp partial outputs through shared memory (reuses the tile area), four
+        // warps at a time
+        constexpr int PM = MT * 16, PN = NT * 8;
+        static_assert((size_t)4 * PM * PN <= (size_t)NW * 2 * 16 * FPS, "dW1 staging fits the tile area");
+        float* part = tiles;                                  // [4][PM][PN]
+#pragma unroll 1
+        for (int half = 0; half < NW / 4; ++half) {
+            __syncthreads();
+            if ((warp >> 2) == half) {
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+                    for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const int f = mt * 16 + g + ((i & 2) ? 8 : 0), e = nt * 8 + 2 * t + (i & 1);
+                            part[((size_t)(warp & 3) * PM + f) * PN + e] = gacc[mt][nt][i];
+                        }
+            }
+            __syncthreads();
+            for (int i = tid; i < F * F; i += kThreads) {
+                const int f = i / F, e = i - f * F;
+                float s = 0.f;
+#pragma unroll
+                for (int qq = 0; qq < 4; ++qq) s += part[((size_t)qq * PM + f) * PN + e];
+                atomicAdd(&dpr[net * o.stride + o.W1 + f * F + e], s);
+            }
+        }
+    }
+}
+
+}  // namespace gwtf
