@@ -164,7 +164,7 @@ def workload_name(args):
                                                                                        args.points)
 
 
-def kernel_only_times(model, p, g, reps):
+def kernel_only_times(model, p, g, reps, keep=None):
     """CUDA-event time of the step's own kernels with nothing in between: forward driver
     (moments + 2 phases x L layers + bstat + nll) and backward driver (seed + 2 phases x L + finish),
     plus each phase class timed over the L layers."""
@@ -184,7 +184,6 @@ def kernel_only_times(model, p, g, reps):
         logits = model.get_weights(g)
         logw = (logits - torch.logsumexp(logits, -1, keepdim=True)).contiguous()
     ubuf = torch.empty(L, K, B, 3, N, device=dev)
-    ybuf = None      # recompute h1 in backward (keeping y1 measured slower; FlowStack.keep_activations)
     ld = torch.zeros(K, B, N, device=dev)
     mom = torch.zeros(L, K, nat.MOM_STRIDE, device=dev, dtype=torch.float64)
     sum1 = torch.zeros(L, K, 2, 2, Fd, device=dev, dtype=torch.float64)
@@ -203,6 +202,10 @@ def kernel_only_times(model, p, g, reps):
     desc = ctypes.byref(stack.desc)
     P = nat.ptr
     n_total = float(B * N)
+    # kept activations follow the product default (FlowStack.keep_activations: on for the mma engine)
+    if keep is None:
+        keep = stack.keep_activations if stack.keep_activations is not None else lib.gwtf_engine() != 0
+    ybuf = torch.empty(int(lib.gwtf_keep_floats(desc, B, N)), device=dev) if keep else None
 
     def fwd():
         nat.check(lib.gwtf_fwd_all(desc, 1, P(params), P(bnbuf), P(film), P(p), P(base), P(logw), P(ubuf), P(ld), None,

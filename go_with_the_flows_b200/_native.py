@@ -24,6 +24,7 @@ _D = ctypes.POINTER(StackDesc)
 _SIGNATURES = {
     'gwtf_version': [],
     'gwtf_set_tensor_cores': [c_i],
+    'gwtf_engine': [],
     'gwtf_rec_stride': [c_i],
     'gwtf_param_offsets': [c_i, c_i, ctypes.POINTER(c_i), ctypes.POINTER(c_i)],
     'gwtf_fma_peak_tflops': [c_i, ctypes.POINTER(c_d), c_f],
@@ -42,7 +43,7 @@ _SIGNATURES = {
                     c_f, c_f, c_f, c_f],
 }
 
-EXPORTED = sorted(_SIGNATURES) + ['gwtf_last_error_string']
+EXPORTED = sorted(_SIGNATURES) + ['gwtf_last_error_string', 'gwtf_keep_floats']
 
 _lib = None
 
@@ -66,6 +67,8 @@ def lib():
             fn.restype = ctypes.c_int
         handle.gwtf_last_error_string.argtypes = []
         handle.gwtf_last_error_string.restype = ctypes.c_char_p
+        handle.gwtf_keep_floats.argtypes = [_D, c_i, c_i]
+        handle.gwtf_keep_floats.restype = ctypes.c_int64
         _lib = handle
     return _lib
 

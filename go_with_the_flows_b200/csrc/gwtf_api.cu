@@ -11,6 +11,7 @@
 #include "gwtf_tc_persist.cuh"
 #include "gwtf_bwd.cuh"
 #include "gwtf_bwd_mma.cuh"
+#include "gwtf_fwd_mma.cuh"
 #include "gwtf_sample.cuh"
 
 using namespace gwtf;
@@ -47,23 +48,26 @@ int check_desc(const gwtf_stack_desc* d) {
 }
 
 int g_use_tc = -1;    // -1: decide from the environment (GWTF_TC), 0 = FMA, 1 = tcgen05 (3 CTAs/SM),
-                      // 2 = tcgen05 persistent warp-specialised (1 CTA/SM, 4 tiles in flight)
+                      // 2 = tcgen05 persistent warp-specialised forward (1 CTA/SM, 4 tiles in flight; default),
+                      // 3 = warp-level mma.sync fragments for the forward too (the backward always uses them)
 
 int tc_mode(int F) {
     if (g_use_tc < 0) {
         const char* e = getenv("GWTF_TC");
-        g_use_tc = e ? (e[0] == '0' ? 0 : (e[0] == '1' ? 1 : 2)) : 2;
+        g_use_tc = e ? (e[0] == '0' ? 0 : (e[0] == '1' ? 1 : (e[0] == '3' ? 3 : 2))) : 2;
     }
-    return F <= 39 ? g_use_tc : 0;      // tensor-memory tile budget: F + 1 (bias channel) <= 40; configs use 33 / 37
+    return g_use_tc;
 }
-bool use_tc(int F) { return tc_mode(F) != 0; }
-// backward contractions on mma.sync register fragments (any F <= 64) unless the FMA engine is selected;
-// GWTF_MMA_BWD=0 keeps the CUDA-core backward for A/B timing
-bool use_mma_bwd() {
-    static int env = -1;
-    if (env < 0) { const char* e = getenv("GWTF_MMA_BWD"); env = (e && e[0] == '0') ? 0 : 1; }
-    return tc_mode(1) != 0 && env != 0;
+// forward engine for feature width F: the tcgen05 kernels need F + 1 <= 40, wider stacks take the mma.sync path
+int fwd_engine(int F) {
+    tc_mode(F);
+    if (g_use_tc == 0 || g_use_tc == 3) return g_use_tc;
+    return F <= 39 ? g_use_tc : 3;
 }
+bool use_tc(int F) { const int m = fwd_engine(F); return m == 1 || m == 2; }
+bool use_mma_fwd(int F) { return fwd_engine(F) == 3; }
+// backward contractions on mma.sync register fragments (any F <= 64) unless the FMA engine is selected
+bool use_mma_bwd() { tc_mode(1); return g_use_tc != 0; }
 
 int padded_features(int F) {
     const int opts[] = {8, 16, 24, 32, 36, 40, 48, 64};
@@ -188,6 +192,41 @@ int launch_fwd_layer_tcp(const LayerArgs& a0, cudaStream_t st) {
 }
 
 template <int FP, int PHASE>
+int launch_fwd_layer_mma(const LayerArgs& a, cudaStream_t st) {
+    // statistics pass: 2 m-tiles per warp (shared B fragments, 2 MMA chains), full register file, 1 CTA/SM;
+    // apply pass: 1 m-tile per warp, 128 registers, 2 CTAs/SM
+    constexpr int MI = PHASE == 0 ? 2 : 1;
+    const int F = a.d.n_features, K = a.d.n_components;
+    const size_t smem = fwd_mma_smem<FP>(F);
+    auto kern = k_fwd_layer_mma<FP, PHASE, MI>;
+    GWTF_CUDA(allow_smem(kern, smem));
+    const long long tiles = (long long)a.B * ((a.N + 128 * MI - 1) / (128 * MI));
+    int gx = (MI == 1 ? 2 : 1) * num_sms() / K;              // contiguous tile ranges
+    if (gx > tiles) gx = (int)tiles;
+    kern<<<dim3(gx < 1 ? 1 : gx, K), kThreads, smem, st>>>(a, PHASE == 1 ? a.y1out : nullptr);
+    GWTF_CUDA(cudaGetLastError());
+    return 0;
+}
+
+#define GWTF_DISPATCH_FP8(F, CALL)                        \
+    switch (((F) + 7) / 8 * 8) {                          \
+        case 8:  { constexpr int FP = 8;  CALL; } break;  \
+        case 16: { constexpr int FP = 16; CALL; } break;  \
+        case 24: { constexpr int FP = 24; CALL; } break;  \
+        case 32: { constexpr int FP = 32; CALL; } break;  \
+        case 40: { constexpr int FP = 40; CALL; } break;  \
+        case 48: { constexpr int FP = 48; CALL; } break;  \
+        case 56: { constexpr int FP = 56; CALL; } break;  \
+        case 64: { constexpr int FP = 64; CALL; } break;  \
+        default: return fail(-4, "unsupported feature width"); \
+    }
+
+// floats per layer of the kept-activation buffer under the current engine
+size_t keep_layer_floats(int F, int K, int B, int N) {
+    return fwd_engine(F) != 0 ? (size_t)K * mma_keep_floats(F, B, N) : (size_t)K * 2 * F * B * N;
+}
+
+template <int FP, int PHASE>
 int launch_fwd_layer(const LayerArgs& a0, cudaStream_t st) {
     constexpr int P = PointsPerThread<FP>::fwd;
     LayerArgs a = a0;
@@ -214,10 +253,17 @@ int gwtf_version(void) { return 1; }
 
 int gwtf_set_tensor_cores(int32_t enable) {
     const int prev = g_use_tc;
-    g_use_tc = enable < 0 ? -1 : (enable > 2 ? 2 : enable);
+    g_use_tc = enable < 0 ? -1 : (enable > 3 ? 3 : enable);
     return prev;
 }
 const char* gwtf_last_error_string(void) { return g_err; }
+
+int gwtf_engine(void) { tc_mode(1); return g_use_tc; }
+
+int64_t gwtf_keep_floats(const gwtf_stack_desc* desc, int32_t B, int32_t N) {
+    if (check_desc(desc) || B <= 0 || N <= 0) return 0;
+    return (int64_t)desc->n_layers * (int64_t)keep_layer_floats(desc->n_features, desc->n_components, B, N);
+}
 
 int gwtf_rec_stride(int32_t F) { return rec_stride_of(F); }
 
@@ -274,7 +320,12 @@ int gwtf_fwd_layer_ex(const gwtf_stack_desc* desc, int32_t layer, int32_t phase,
     a.d = *desc; a.layer = layer; a.train = train; a.direct = direct; a.params = params; a.bnbuf = bnbuf; a.film = film;
     a.xin = xin; a.xin_shared = xin_shared; a.xout = xout; a.ld = ld; a.ssum = ssum; a.trio = trio; a.y1out = y1out;
     a.mom_in = mom_in; a.mom_out = mom_out; a.sum1 = sum1; a.B = B; a.N = N; a.n_total = n_total; a.tiles_per_shape = 0;
-    if (tc_mode(desc->n_features) == 2 && desc->n_components <= num_sms()) {
+    if (use_mma_fwd(desc->n_features)) {
+        if (phase == 0) { GWTF_DISPATCH_FP8(desc->n_features, return (launch_fwd_layer_mma<FP, 0>(a, (cudaStream_t)stream))); }
+        else { GWTF_DISPATCH_FP8(desc->n_features, return (launch_fwd_layer_mma<FP, 1>(a, (cudaStream_t)stream))); }
+        return 0;
+    }
+    if (fwd_engine(desc->n_features) == 2 && desc->n_components <= num_sms()) {
         if (phase == 0) { GWTF_DISPATCH_TC(desc->n_features, return (launch_fwd_layer_tcp<FPK, FPN, 0>(a, (cudaStream_t)stream))); }
         else { GWTF_DISPATCH_TC(desc->n_features, return (launch_fwd_layer_tcp<FPK, FPN, 1>(a, (cudaStream_t)stream))); }
         return 0;
@@ -302,7 +353,7 @@ int gwtf_fwd_layer(const gwtf_stack_desc* desc, int32_t layer, int32_t phase, in
     double* mom_in = mom ? mom + (size_t)layer * K * GWTF_MOM_STRIDE : nullptr;
     double* mom_out = (mom && layer > 0) ? mom + (size_t)(layer - 1) * K * GWTF_MOM_STRIDE : nullptr;
     double* s1 = sum1 ? sum1 + (size_t)layer * K * 4 * F : nullptr;
-    float* y1 = ybuf ? ybuf + (size_t)layer * K * 2 * F * B * N : nullptr;
+    float* y1 = ybuf ? ybuf + (size_t)layer * keep_layer_floats(F, K, B, N) : nullptr;
     return gwtf_fwd_layer_ex(desc, layer, phase, train, 0, params, bnbuf, film, xin, first ? 1 : 0,
                              ubuf + (size_t)layer * slot, ld, ssum, nullptr, y1, mom_in, train ? mom_out : nullptr, s1,
                              B, N, n_total, stream);

@@ -2,6 +2,7 @@
 // (activations are recomputed from the saved layer inputs, never stored), closed-form finish.
 #pragma once
 #include "gwtf_common.cuh"
+#include "gwtf_mma.cuh"
 
 namespace gwtf {
 
@@ -59,7 +60,8 @@ struct BwdArgs {
     const float* xin;        // input of the layer: (K,B,3,N) or the (B,3,N) data cloud
     int xin_shared;
     const float* xout;       // output of the layer = ubuf[layer] (K,B,3,N)
-    const float* y1in;       // (K,2,F,B,N) kept by the forward apply pass, or null: recompute h1
+    const float* y1in;       // kept by the forward apply pass (layout private to the engine), or null: recompute h1
+    int kept_y1;             // mma kernels: the kept buffer holds y1 = s*n1 + t (tcgen05 forward) instead of h1
     const double* mom_in;    // (K,16) moments of the layer input
     const double* sum1;      // (K,2,2,F)
     double* bsum;            // (K,2,4,F) this layer: sum dn1 | sum dn1*n1 | sum dy0 | sum dy0*hhat0
@@ -124,6 +126,7 @@ struct BwdSmem {
     uint64_t bar;
     float corr[12];
     float red[2][round_up(5 * FP + 3, 32)];
+    float2 mif[2][FP];      // mma phase 0: n1 = v*mif.y - mif.x for the value v read/recomputed (h1 or kept y1)
 };
 
 // ---- PHASE 0: d(o_mu,o_lv), FiLM + sd2 gradients, sd1_bn backward sums ------------------------
@@ -339,10 +342,6 @@ __device__ __forceinline__ void mma_m16n8k8_tf32(float (&d)[4], const uint32_t (
     asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                  : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
-}
-__device__ __forceinline__ void split_tf32_bits(float x, uint32_t& hi, uint32_t& lo) {
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
-    lo = __float_as_uint(x - __uint_as_float(hi));
 }
 
 // ---- PHASE 1: sd1 / sd0 / bn0 gradients and the input gradient --------------------------------

@@ -17,24 +17,9 @@
 #pragma once
 #include "gwtf_bwd.cuh"
 #include "gwtf_tc.cuh"
+#include "gwtf_mma.cuh"
 
 namespace gwtf {
-
-__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-    asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
-
-__device__ __forceinline__ void mma_tf32p(float* d, const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-    asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
-
-// row stride of the per-warp transpose tiles: == 8 (mod 16) makes the k-major fragment loads of MMA #3
-// and the float2 stores of the C fragments conflict-free
-__host__ __device__ constexpr int mma_tile_stride(int FP) { return (FP % 16 == 8) ? FP : FP + 8; }
 
 template <int FP>
 struct BwdEMmaSmem {
@@ -123,6 +108,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_bwd_layer_e_mma(const BwdArgs a
     const long long total_tiles = (long long)B * tps;
     const int t_begin = (int)(total_tiles * blockIdx.x / gridDim.x);
     const int t_end = (int)(total_tiles * (blockIdx.x + 1) / gridDim.x);
+    const size_t npad = keep_npad(N);
 
 #pragma unroll 1
     for (int net = 0; net < 2; ++net) {
@@ -154,7 +140,8 @@ __global__ void __launch_bounds__(kThreads, 2) k_bwd_layer_e_mma(const BwdArgs a
 #pragma unroll 1
         for (int tile = t_begin; tile < t_end; ++tile) {
             const int b = tile / tps;
-            const int n0 = (tile - b * tps) * TILE + warp * 16;
+            const int tin = tile - b * tps;
+            const int n0 = tin * TILE + warp * 16;
             if (b != cur_b) {
                 __syncthreads();
                 if (tid < FP) {
@@ -167,7 +154,10 @@ __global__ void __launch_bounds__(kThreads, 2) k_bwd_layer_e_mma(const BwdArgs a
                         const float2 ab = S.WB.ab1[net][f];
                         const float4 w2 = S.W.w2[net][f];
                         const float sc = s * mi.y;
-                        c1 = make_float4(sc, tt - s * mi.x, -mi.y * mi.y * ab.y, mi.y * (mi.x * ab.y - ab.x));
+                        if (a.kept_y1)      // the kept value is y1 itself: n1 = (y1 - t) / s
+                            c1 = make_float4(1.f, 0.f, -mi.y * ab.y / s, mi.y * (ab.y * tt / s - ab.x));
+                        else
+                            c1 = make_float4(sc, tt - s * mi.x, -mi.y * mi.y * ab.y, mi.y * (mi.x * ab.y - ab.x));
                         c2 = make_float4(w2.x * sc, w2.y * sc, w2.z * sc, 0.f);
                     }
                     S.cf1[f] = c1;
@@ -193,10 +183,15 @@ __global__ void __launch_bounds__(kThreads, 2) k_bwd_layer_e_mma(const BwdArgs a
                 }
                 gold[r] = (valid[r] && t < 3) ? a.gbuf[sb + (size_t)t * N + n] : 0.f;
             }
-            // ---- a0 (A fragments) and MMA #1: h1[row][f]
+            // ---- a0 (A fragments) and MMA #1: h1[row][f]  (or h1 kept by the forward pass)
             float h[NT][4];
+            const bool kept = a.y1in != nullptr;
+            if (kept) {
+                load_h1_frag<NT>(a.y1in + keep_slab(F, B, N, j, net), (size_t)b * npad + n0, lane, h);
+            } else {
 #pragma unroll
-            for (int nt = 0; nt < NT; ++nt) h[nt][0] = h[nt][1] = h[nt][2] = h[nt][3] = 0.f;
+                for (int nt = 0; nt < NT; ++nt) h[nt][0] = h[nt][1] = h[nt][2] = h[nt][3] = 0.f;
+            }
             uint32_t mask0 = 0u, mask1 = 0u;                  // [y0 > 0] of rows g, g+8; bit = 2ks+i
 #pragma unroll
             for (int ks = 0; ks < KS; ++ks) {
@@ -215,18 +210,20 @@ __global__ void __launch_bounds__(kThreads, 2) k_bwd_layer_e_mma(const BwdArgs a
                 av[3] = valid[1] ? fmaxf(av[3], 0.f) : 0.f;
                 *reinterpret_cast<float2*>(Aw + g * FPS + 8 * ks + 2 * t) = make_float2(av[0], av[2]);
                 *reinterpret_cast<float2*>(Aw + (g + 8) * FPS + 8 * ks + 2 * t) = make_float2(av[1], av[3]);
-                uint32_t ah[4], al[4];
+                if (!kept) {
+                    uint32_t ah[4], al[4];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) split_tf32_bits(av[i], ah[i], al[i]);
-                float4 bq[NT];
+                    for (int i = 0; i < 4; ++i) split_tf32_bits(av[i], ah[i], al[i]);
+                    float4 bq[NT];
 #pragma unroll
-                for (int nt = 0; nt < NT; ++nt) bq[nt] = bf1[(ks * NT + nt) * 32 + lane];
+                    for (int nt = 0; nt < NT; ++nt) bq[nt] = bf1[(ks * NT + nt) * 32 + lane];
 #pragma unroll
-                for (int nt = 0; nt < NT; ++nt) mma_tf32(h[nt], ah, __float_as_uint(bq[nt].x), __float_as_uint(bq[nt].y));
+                    for (int nt = 0; nt < NT; ++nt) mma_tf32(h[nt], ah, __float_as_uint(bq[nt].x), __float_as_uint(bq[nt].y));
 #pragma unroll
-                for (int nt = 0; nt < NT; ++nt) mma_tf32(h[nt], al, __float_as_uint(bq[nt].x), __float_as_uint(bq[nt].y));
+                    for (int nt = 0; nt < NT; ++nt) mma_tf32(h[nt], al, __float_as_uint(bq[nt].x), __float_as_uint(bq[nt].y));
 #pragma unroll
-                for (int nt = 0; nt < NT; ++nt) mma_tf32(h[nt], ah, __float_as_uint(bq[nt].z), __float_as_uint(bq[nt].w));
+                    for (int nt = 0; nt < NT; ++nt) mma_tf32(h[nt], ah, __float_as_uint(bq[nt].z), __float_as_uint(bq[nt].w));
+                }
             }
             // ---- h1 -> dh1 on the C fragments: h[nt][2r+i] = (row g+8r, f = 8nt+2t+i)
 #pragma unroll
@@ -502,18 +499,12 @@ __global__ void __launch_bounds__(kThreads, 2) k_bwd_layer_d_mma(const BwdArgs a
     const long long total_tiles = (long long)B * tps;
     const int t_begin = (int)(total_tiles * blockIdx.x / gridDim.x);
     const int t_end = (int)(total_tiles * (blockIdx.x + 1) / gridDim.x);
+    const size_t npad = keep_npad(N);
 
 #pragma unroll 1
     for (int net = 1; net >= 0; --net) {
         __syncthreads();
-        for (int i = tid; i < KS * NT * 32; i += kThreads) {
-            const int ln = i & 31, nt = (i >> 5) % NT, ks = (i >> 5) / NT;
-            const int gg = ln >> 2, tt = ln & 3;
-            uint32_t h0, l0, h1, l1;
-            split_tf32_bits(S.W.W1T[net][8 * ks + 2 * tt][8 * nt + gg], h0, l0);
-            split_tf32_bits(S.W.W1T[net][8 * ks + 2 * tt + 1][8 * nt + gg], h1, l1);
-            bf1[i] = make_float4(__uint_as_float(h0), __uint_as_float(h1), __uint_as_float(l0), __uint_as_float(l1));
-        }
+        if (!a.y1in) stage_bfrag_h1<FP>(bf1, S.W.W1T[net], tid, kThreads);
         float acc[NT][2][5];                                  // (ds, dt, dW2 xyz) of f = 8nt+2t+i, this lane's rows
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt)
@@ -581,26 +572,35 @@ __global__ void __launch_bounds__(kThreads, 2) k_bwd_layer_d_mma(const BwdArgs a
 #pragma unroll 1
         for (int tile = t_begin; tile < t_end; ++tile) {
             const int b = tile / tps;
-            const int n0 = (tile - b * tps) * TILE + warp * 16;
+            const int tin = tile - b * tps;
+            const int n0 = tin * TILE + warp * 16;
             if (b != cur_b) {
                 if (cur_b >= 0) flush(cur_b);
                 else __syncthreads();
-                stage_film<FP, true>(S.W, &S.WB, a.film + ((size_t)(b * K + j) * L + l) * 4 * F, F, tid, kThreads);
+                const float* film = a.film + ((size_t)(b * K + j) * L + l) * 4 * F;
+                stage_film<FP, true>(S.W, &S.WB, film, F, tid, kThreads);
+                __syncthreads();
+                // per-shape view of the value v the tile loop works on: v = h1 (y1 = st.x v + st.y,
+                // n1 = v istd - mean istd), or v = kept y1 (y1 = v, n1 = (v - t) / s)
+                for (int i = tid; i < 2 * FP; i += kThreads) {
+                    const int nn = i / FP, c = i - nn * FP;
+                    float2 mf = S.W.mi1[nn][c];
+                    if (a.kept_y1) {
+                        const float s = c < F ? film[nn * 2 * F + c] : 0.f, tt = c < F ? film[nn * 2 * F + F + c] : 0.f;
+                        mf = c < F ? make_float2(tt / s, 1.0f / s) : make_float2(0.f, 0.f);
+                        S.W.st[nn][c] = c < F ? make_float2(1.f, 0.f) : make_float2(0.f, 0.f);
+                    }
+                    S.mif[nn][c] = mf;
+                }
                 __syncthreads();
                 cur_b = b;
             }
             const float* xin = a.xin_shared ? a.xin + (size_t)b * 3 * N : a.xin + ((size_t)j * B + b) * 3 * N;
             const size_t sb = ((size_t)j * B + b) * 3 * N;
             float* dob = a.dobuf + ((size_t)j * B + b) * 6 * N;
-            float x[2][3];
             bool valid[2];
 #pragma unroll
-            for (int r = 0; r < 2; ++r) {
-                const int n = n0 + g + 8 * r;
-                valid[r] = n < N;
-#pragma unroll
-                for (int d = 0; d < 3; ++d) x[r][d] = valid[r] ? xin[(size_t)d * N + n] : 0.f;
-            }
+            for (int r = 0; r < 2; ++r) valid[r] = n0 + g + 8 * r < N;
             float outd[2] = {0.f, 0.f}, gcd[2] = {0.f, 0.f}, gsd[2] = {0.f, 0.f};   // dimension td of this lane
             float dO[2][3];
             if (net == 1) {
@@ -622,31 +622,18 @@ __global__ void __launch_bounds__(kThreads, 2) k_bwd_layer_d_mma(const BwdArgs a
                     for (int d = 0; d < 3; ++d) dO[r][d] = valid[r] ? dob[(size_t)d * N + n] : 0.f;
                 }
             }
-            // ---- a0 (A fragments) and h1 = a0 W1^T
             float h[NT][4];
+            if (a.y1in) {
+                load_h1_frag<NT>(a.y1in + keep_slab(F, B, N, j, net), (size_t)b * npad + n0, lane, h);
+            } else {
+                float x[2][3];
 #pragma unroll
-            for (int nt = 0; nt < NT; ++nt) h[nt][0] = h[nt][1] = h[nt][2] = h[nt][3] = 0.f;
+                for (int r = 0; r < 2; ++r) {
+                    const int n = n0 + g + 8 * r;
 #pragma unroll
-            for (int ks = 0; ks < KS; ++ks) {
-                const float4 qa = S.W.q0[net][8 * ks + 2 * t];
-                const float4 qb = S.W.q0[net][8 * ks + 2 * t + 1];
-                float av[4];
-                av[0] = fmaxf(fmaf(qa.x, x[0][0], fmaf(qa.y, x[0][1], fmaf(qa.z, x[0][2], qa.w))), 0.f);
-                av[1] = fmaxf(fmaf(qa.x, x[1][0], fmaf(qa.y, x[1][1], fmaf(qa.z, x[1][2], qa.w))), 0.f);
-                av[2] = fmaxf(fmaf(qb.x, x[0][0], fmaf(qb.y, x[0][1], fmaf(qb.z, x[0][2], qb.w))), 0.f);
-                av[3] = fmaxf(fmaf(qb.x, x[1][0], fmaf(qb.y, x[1][1], fmaf(qb.z, x[1][2], qb.w))), 0.f);
-                uint32_t ah[4], al[4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) split_tf32_bits(av[i], ah[i], al[i]);
-                float4 bq[NT];
-#pragma unroll
-                for (int nt = 0; nt < NT; ++nt) bq[nt] = bf1[(ks * NT + nt) * 32 + lane];
-#pragma unroll
-                for (int nt = 0; nt < NT; ++nt) mma_tf32(h[nt], ah, __float_as_uint(bq[nt].x), __float_as_uint(bq[nt].y));
-#pragma unroll
-                for (int nt = 0; nt < NT; ++nt) mma_tf32(h[nt], al, __float_as_uint(bq[nt].x), __float_as_uint(bq[nt].y));
-#pragma unroll
-                for (int nt = 0; nt < NT; ++nt) mma_tf32(h[nt], ah, __float_as_uint(bq[nt].z), __float_as_uint(bq[nt].w));
+                    for (int d = 0; d < 3; ++d) x[r][d] = valid[r] ? xin[(size_t)d * N + n] : 0.f;
+                }
+                mma_h1<FP>(S.W.q0[net], bf1, x, valid, lane, h);
             }
             if (net == 1) {
                 // head: o_lv = W2 relu(y1) + b2 (partial over this lane's channels, then over the 4 lanes)
@@ -701,7 +688,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_bwd_layer_d_mma(const BwdArgs a
 #pragma unroll
                 for (int i = 0; i < 2; ++i) {
                     const float2 st = S.W.st[net][8 * nt + 2 * t + i];
-                    const float2 mi = S.W.mi1[net][8 * nt + 2 * t + i];
+                    const float2 mi = S.mif[net][8 * nt + 2 * t + i];
                     const float4 w2 = S.W.w2[net][8 * nt + 2 * t + i];
 #pragma unroll
                     for (int r = 0; r < 2; ++r) {

@@ -15,6 +15,7 @@
 #pragma once
 #include "gwtf_fwd.cuh"
 #include "gwtf_tc.cuh"
+#include "gwtf_mma.cuh"
 
 namespace gwtf {
 
@@ -141,16 +142,27 @@ __device__ __forceinline__ void issue_ss_k8(uint32_t d_tmem, const float* x_hi, 
 
 // all threads: relu the accumulator row of this thread and write it back as the next A operand
 // (all FPK columns are loaded in one go so the TMEM read latency is paid once, not per chunk)
+// base address of point (b, n) in the kept-activation buffer (gwtf_mma.cuh), or null
+__device__ __forceinline__ float* keep_ptr(float* keep, int j, int net, int F, int B, int N, int b, int n) {
+    if (!keep) return nullptr;
+    return keep + keep_slab(F, B, N, j, net) + keep_point_base((size_t)b * keep_npad(N) + n, (F + 7) / 8);
+}
+
 template <int FPK, int FPN>
-__device__ __forceinline__ void relu_to_operand(uint32_t trow, float* keep = nullptr, size_t keep_stride = 0, int F = 0) {
+__device__ __forceinline__ void relu_to_operand(uint32_t trow, float* keepf = nullptr, int keep_nt = 0, bool valid = true) {
     using C = TcCols<FPK, FPN>;
     float y[FPK];
     tmem_ld<FPK>(trow + C::D, y);
     tmem_wait_ld();
-    if (keep) {     // y1 of this thread's point, one coalesced store per channel
+    if (keepf) {
+        // y1 of this thread's point kept for the backward pass in MMA C-fragment order; rows beyond N hold zeros
 #pragma unroll
-        for (int f = 0; f < FPK; ++f)
-            if (f < F) keep[(size_t)f * keep_stride] = y[f];
+        for (int nt = 0; nt < FPK / 8; ++nt)
+            if (nt < keep_nt)
+#pragma unroll
+                for (int tt = 0; tt < 4; ++tt)
+                    *reinterpret_cast<float2*>(keepf + (nt * 32 + tt) * 4) =
+                        valid ? make_float2(y[8 * nt + 2 * tt], y[8 * nt + 2 * tt + 1]) : make_float2(0.f, 0.f);
     }
 #pragma unroll
     for (int c = 0; c < FPK; c += 8) {
@@ -352,8 +364,7 @@ __global__ void __launch_bounds__(kTcThreads) k_fwd_layer_tc(const LayerArgs a) 
             for (int net = 0; net < 2; ++net) {
                 run_to_h1<FPK, FPN>(S, net, tbase, trow, mma_phase, tid);
                 GWTF_T(5);
-                relu_to_operand<FPK, FPN>(trow, (a.y1out && valid) ? a.y1out + ((((size_t)j * 2 + net) * F) * B + b) * N + n : nullptr,
-                                          (size_t)B * N, F);
+                relu_to_operand<FPK, FPN>(trow, keep_ptr(a.y1out, j, net, F, B, N, b, n), (F + 7) / 8, valid);
                 tc_handoff();
                 GWTF_T(7);
                 if (tid == 0) {

@@ -220,8 +220,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) k_fwd_layer_tcp(const Laye
                     relu_to_operand<FPK, FPN>(trow);
                     request();                                      // -> MMA1
                     wait_done();                                    // y1
-                    relu_to_operand<FPK, FPN>(trow, (a.y1out && valid) ? a.y1out + ((((size_t)j * 2 + net) * F) * B + b) * N + n : nullptr,
-                                              (size_t)B * N, F);
+                    relu_to_operand<FPK, FPN>(trow, keep_ptr(a.y1out, j, net, F, B, N, b, n), (F + 7) / 8, valid);
                     request();                                      // -> MMA2
                     wait_done();                                    // o
                     float ov[8];

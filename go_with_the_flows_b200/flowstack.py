@@ -132,10 +132,13 @@ class FlowStack:
             self.desc.warp_mask[l] = mask
         self.sync_gradients = True
         self._n_total_cache = {}
-        # keep y1 (296 B per point/component/layer at F=37) from the apply pass so that backward skips one
-        # contraction per phase; measured SLOWER than recomputing on B200 (r01: 309/429 us vs 214/380 us per
-        # backward launch), so it is off by default
-        self.keep_activations = False
+        # keep the sd1 output of every layer/net from the forward apply pass so that the backward phases
+        # skip one F x F contraction each (320 B per point/component/layer at F=37: 5.5 GB for 64 x 2048
+        # points).  None = automatic: on for the tensor-core engines (fragment-ordered buffer, coalesced
+        # 16-byte accesses), off for the FMA engine where recomputing measured faster (r01: 309/429 us vs
+        # 214/380 us per backward launch)
+        self.keep_activations = None
+        self._keep_pool = {}
         self.C = self.K * self.L * 4
         if self.flat:
             self._build_layout()
@@ -489,13 +492,22 @@ class _StackNLLPass(torch.autograd.Function):
         ld = torch.zeros(K, B, N, device=dev)
         mom = sum1 = bstat = None
         n_total = float(B * N)
-        # y1 of every layer/net kept for backward (skips one F x F contraction in each backward phase)
+        # activations kept for backward (layout private to the engine, sized by the library)
         ybuf = None
-        if stack.keep_activations:
-            need = L * K * 2 * Fd * B * N * 4
-            free, _ = torch.cuda.mem_get_info(dev)
-            if need < 0.5 * free + torch.cuda.memory_reserved(dev) - torch.cuda.memory_allocated(dev):
-                ybuf = torch.empty(L, K, 2, Fd, B, N, device=dev)
+        keep = stack.keep_activations
+        if keep is None:
+            keep = lib.gwtf_engine() != 0 and any(ctx.needs_input_grad)
+        if keep:
+            # multi-GB scratch: recycled through a per-stack pool (returned by backward) so that the
+            # caching allocator never splits or re-mallocs it between steps
+            need = int(lib.gwtf_keep_floats(desc, B, N))
+            pool = stack._keep_pool.setdefault((need, dev), [])
+            if pool:
+                ybuf = pool.pop()
+            else:
+                free, _ = torch.cuda.mem_get_info(dev)
+                if 4 * need < 0.5 * free + torch.cuda.memory_reserved(dev) - torch.cuda.memory_allocated(dev):
+                    ybuf = torch.empty(need, device=dev)
         if training:
             mom = torch.zeros(L, K, nat.MOM_STRIDE, device=dev, dtype=torch.float64)
             sum1 = torch.zeros(L, K, 2, 2, Fd, device=dev, dtype=torch.float64)
@@ -567,6 +579,9 @@ class _StackNLLPass(torch.autograd.Function):
             nat.check(lib.gwtf_bwd_finish(desc, train, nat.ptr(params), nat.ptr(bnbuf), nat.ptr(mom), nat.ptr(bsum),
                                           nat.ptr(gbuf), nat.ptr(p), nat.ptr(dparams), nat.ptr(dpoints), B, N,
                                           ctx.n_total, st), 'gwtf_bwd_finish')
+        if ybuf is not None:            # stream-ordered reuse: the next forward runs after these launches
+            stack._keep_pool.setdefault((ybuf.numel(), dev), []).append(ybuf)
+            ctx.ybuf = None
         return dpoints, dparams, dfilm, None, None, None, None
 
 

@@ -57,11 +57,23 @@ typedef struct gwtf_stack_desc {
 } gwtf_stack_desc;
 
 int gwtf_version(void);
-/* Contraction engine of the per-layer forward kernels: 2 = tcgen05 tensor cores, persistent
- * warp-specialised kernel (default; 3xTF32, TMEM accumulators, feature widths <= 39), 1 = tcgen05
- * with one tile per 128-thread CTA, 0 = FP32 FMA pipe, -1 = re-read the GWTF_TC environment variable.
+/* Contraction engine of the per-layer kernels:
+ *   3 = warp-level tensor-core fragments (mma.sync m16n8k8 tf32, 3xTF32) for the forward AND backward
+ *       layer phases, feature widths <= 64 (what engines 1-2 fall back to for widths > 39);
+ *   2 = tcgen05 tensor cores for the forward phases, persistent warp-specialised kernel (3xTF32, TMEM
+ *       accumulators, feature widths <= 39) + the mma.sync backward (default);
+ *   1 = tcgen05 forward with one tile per 128-thread CTA + the mma.sync backward;
+ *   0 = FP32 FMA pipe everywhere;  -1 = re-read the GWTF_TC environment variable.
  * Returns the previous setting (NOT an error code). */
 int gwtf_set_tensor_cores(int32_t enable);
+/* The engine currently selected (0..3, environment resolved). */
+int gwtf_engine(void);
+/* Size in floats of the optional kept-activation buffer (`ybuf` of gwtf_fwd_layer / gwtf_fwd_all /
+ * gwtf_bwd_layer / gwtf_bwd_all) for B clouds of N points under the CURRENT engine; the layout is private
+ * to the engine, so the forward and backward calls that share a buffer must run under the same setting.
+ * The tensor-core engines keep the sd1 output (engine 3: before, engines 1-2: after sd1_bn + FiLM, flows.py:100-104)
+ * in MMA-fragment order: L*K*2*B*ceil(N/256)*256*roundup8(F) floats. */
+int64_t gwtf_keep_floats(const gwtf_stack_desc* desc, int32_t B, int32_t N);
 const char* gwtf_last_error_string(void);
 
 /* Record geometry shared with the Python packer.  offsets[0..5] = W0,bn0.weight,bn0.bias,W1,W2,b2

@@ -9,11 +9,11 @@ from tests.util import max_rel, nll_err, rel_l2
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=['tcgen05_persistent', 'tcgen05', 'fma'], autouse=True)
+@pytest.fixture(params=['mma', 'tcgen05_persistent', 'tcgen05', 'fma'], autouse=True)
 def contraction_engine(request):
     from go_with_the_flows_b200 import _native
     lib = _native.lib()
-    prev = lib.gwtf_set_tensor_cores({'tcgen05_persistent': 2, 'tcgen05': 1, 'fma': 0}[request.param])
+    prev = lib.gwtf_set_tensor_cores({'mma': 3, 'tcgen05_persistent': 2, 'tcgen05': 1, 'fma': 0}[request.param])
     yield request.param
     lib.gwtf_set_tensor_cores(prev)
 

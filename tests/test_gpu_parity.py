@@ -12,13 +12,13 @@ from tests.util import GOLDEN_CASES, Golden, build_dropin, max_rel
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=['tcgen05_persistent', 'tcgen05', 'fma'], autouse=True)
+@pytest.fixture(params=['mma', 'tcgen05_persistent', 'tcgen05', 'fma'], autouse=True)
 def contraction_engine(request):
     """Every GPU parity test runs on both engines of the per-layer kernels: tcgen05 tensor cores
     (3xTF32, default) and the FP32 FMA pipe."""
     from go_with_the_flows_b200 import _native
     lib = _native.lib()
-    prev = lib.gwtf_set_tensor_cores({'tcgen05_persistent': 2, 'tcgen05': 1, 'fma': 0}[request.param])
+    prev = lib.gwtf_set_tensor_cores({'mma': 3, 'tcgen05_persistent': 2, 'tcgen05': 1, 'fma': 0}[request.param])
     yield request.param
     lib.gwtf_set_tensor_cores(prev)
 
@@ -196,8 +196,10 @@ def test_two_gpu_syncbn_equals_concatenated_batch():
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
 
 
-def test_kept_activations_path_matches():
-    """Optional path: y1 kept by the apply pass instead of recomputed in backward."""
+@pytest.mark.parametrize('keep', [True, False])
+def test_kept_activations_path_matches(keep):
+    """Both backward variants: activations kept by the forward apply pass, or recomputed (the default
+    depends on the engine)."""
     gd = Golden('small_free_learned')
     noise = parity.oracle_fp32_errors(gd, 'train')
     import go_with_the_flows_b200.flowstack as fs
@@ -205,7 +207,7 @@ def test_kept_activations_path_matches():
 
     def patched(self, *a, **k):
         orig(self, *a, **k)
-        self.keep_activations = True
+        self.keep_activations = keep
     fs.FlowStack.__init__ = patched
     try:
         res = parity.dropin_nll_errors(gd, 'train', fused_nll=True)
