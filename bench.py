@@ -241,9 +241,10 @@ def kernel_only_times(model, p, g, reps, keep=None):
             best.append(e0.elapsed_time(e1))
         return sum(best) / len(best)
 
-    out = {'fwd_ms': timed(fwd), 'bwd_ms': timed(bwd)}
+    out = {'fwd_ms': timed(fwd), 'bwd_ms': timed(bwd), 'kept': bool(keep), 'kept_bytes': 4 * ybuf.numel() if keep else 0}
     for name, kind, phase in (('fwd_stats', 'fwd', 0), ('fwd_apply', 'fwd', 1), ('bwd_d', 'bwd', 0), ('bwd_e', 'bwd', 1)):
         out[name + '_ms_per_launch'] = timed(lambda: phase_loop(kind, phase)) / L
+    del ybuf
     return out
 
 
@@ -399,6 +400,10 @@ def main():
         kt = kernel_only_times(model, p_dev, g_dev, reps=3)
         peak = ctypes.c_double(0.0)
         nat.check(nat.lib().gwtf_fma_peak_tflops(20000, ctypes.byref(peak), None), 'gwtf_fma_peak_tflops')
+        mma_peak = ctypes.c_double(0.0)
+        nat.check(nat.lib().gwtf_mma_peak_tflops(4000, ctypes.byref(mma_peak), None), 'gwtf_mma_peak_tflops')
+        engine = int(nat.lib().gwtf_engine())
+        kept = bool(kt['kept'])
         kernel_ms = kt['fwd_ms'] + kt['bwd_ms']
         achieved = B * N * fl_step / (kernel_ms * 1e-3) * 1e-12
         per_pc_layer = 4 * (Fd * Fd + 3 * Fd)      # fwd FLOPs per point, component, layer
@@ -406,11 +411,23 @@ def main():
         # algorithmic share of each launch class (recomputation earns nothing)
         alg = {'fwd_stats': 0.0, 'fwd_apply': per_pc_layer * launch_units, 'bwd_d': 4 * Fd * 3 * launch_units,
                'bwd_e': (2 * per_pc_layer - 4 * Fd * 3) * launch_units}
+        # F x F contractions each launch class executes per point, component and net
+        executed = {'fwd_stats': 1, 'fwd_apply': 1, 'bwd_d': 0 if kept else 1, 'bwd_e': 2 if kept else 3}
         kernels = {}
         for name in ('fwd_stats', 'fwd_apply', 'bwd_d', 'bwd_e'):
             ms = kt[name + '_ms_per_launch']
             kernels[name] = {'ms_per_launch': ms, 'algorithmic_tflops': alg[name] / (ms * 1e-3) * 1e-12,
-                             'executed_contractions': {'fwd_stats': 1, 'fwd_apply': 1, 'bwd_d': 1, 'bwd_e': 3}[name]}
+                             'executed_contractions': executed[name]}
+        # tensor-pipe work of the dominant kernel: m16n8k8 tf32 MMAs per 16-point tile and net (F padded to 8,
+        # the dW1 output to 16 rows), three per product (3xTF32)
+        f8, f16 = (Fd + 7) // 8, (Fd + 15) // 16
+        mma_per_tile = 3 * ((executed['bwd_e'] - 1) * f8 * f8 + 2 * f16 * f8)
+        e_tensor_tflops = mma_per_tile * 2048.0 * (launch_units / 16.0) * 2 / (kernels['bwd_e']['ms_per_launch'] * 1e-3) * 1e-12
+        traffic = None
+        tpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'profiles', 'r01_ncu_traffic.json')
+        if os.path.exists(tpath) and args.config == 'generative' and B == 64 and N == 2048:
+            with open(tpath) as fh:       # dram bytes per launch of the dominant kernel from the committed ncu capture
+                traffic = json.load(fh).get('k_bwd_layer_e_mma', {}).get('kept' if kept else 'recompute')
         dom = kernels['bwd_e']
         line = {
             'metric': 'points/sec fwd+bwd mixture-flow NLL', 'value': value, 'unit': 'points/s', 'n_gpus': world,
@@ -423,17 +440,28 @@ def main():
             'e2e': {'value': e2e_value, 'unit': 'points/s', 'h2d_bytes_per_step': world * (p_host.numel() + g_host.numel()) * 4,
                     'd2h_bytes_per_step': world * 4, 'ms_per_step': e2e_ms / args.steps},
             'gpu_launches': args.steps * (4 * L + 6),
-            'roofline': {'bound': 'fma', 'kernel': 'k_bwd_layer_e (dominant; per launch = one coupling layer, all K components)',
-                         'achieved': dom['algorithmic_tflops'], 'peak': peak.value, 'unit': 'TFLOP/s',
-                         'frac': dom['algorithmic_tflops'] / peak.value, 'traffic': None,
-                         'peak_source': 'FP32 FFMA probe kernel measured live on this GPU (MEASURED_PEAKS.json has no fp32 entry)',
+            'roofline': {'bound': 'tensor',
+                         'kernel': 'k_bwd_layer_e_mma (dominant; per launch = one coupling layer, all K components)',
+                         'achieved': dom['algorithmic_tflops'], 'peak': mma_peak.value / 3.0, 'unit': 'TFLOP/s',
+                         'frac': dom['algorithmic_tflops'] / (mma_peak.value / 3.0), 'traffic': traffic,
+                         'peak_source': 'fp32-grade contractions run as 3xTF32 on mma.sync: peak = dense TF32 mma.sync '
+                                        'throughput measured live by gwtf_mma_peak_tflops (%.1f TFLOP/s) / 3; '
+                                        'MEASURED_PEAKS.json only holds the bf16 cuBLAS figure, which no fp32-parity '
+                                        'path can use' % mma_peak.value,
+                         'tensor_pipe': {'executed_tf32_tflops': e_tensor_tflops, 'mma_sync_tf32_peak': mma_peak.value,
+                                         'frac': e_tensor_tflops / mma_peak.value},
+                         'fma_peak': peak.value, 'frac_of_fma_peak': dom['algorithmic_tflops'] / peak.value,
                          'step': {'kernel_ms': kernel_ms, 'fwd_ms': kt['fwd_ms'], 'bwd_ms': kt['bwd_ms'],
-                                  'achieved': achieved, 'frac': achieved / peak.value,
-                                  'flops_per_point': fl_step},
+                                  'achieved': achieved, 'frac': achieved / (mma_peak.value / 3.0),
+                                  'frac_of_fma_peak': achieved / peak.value, 'flops_per_point': fl_step},
                          'kernels': kernels},
             'clocks': clocks,
-            'engine': 'tcgen05 3xTF32 forward layer kernels + fp32 FMA backward / fused-eval / sampling kernels'
-                      if os.environ.get('GWTF_TC', '1') != '0' and Fd <= 39 else 'fp32 FMA kernels',
+            'engine': {0: 'fp32 FMA kernels',
+                       1: 'tcgen05 3xTF32 forward (one tile per CTA) + mma.sync 3xTF32 backward',
+                       2: 'tcgen05 3xTF32 persistent warp-specialised forward + mma.sync 3xTF32 backward',
+                       3: 'mma.sync 3xTF32 forward and backward'}[engine] +
+                      ('; sd1 outputs kept for backward (%.1f GB)' % (kt['kept_bytes'] / 1e9) if kept else '; backward recomputes h1') +
+                      '; fp32 FMA fused-eval / sampling kernels',
             'extra': side_workloads(model, cfg, dev, N),
         }
         if not args.no_cpu_baseline and world == 1:

@@ -13,8 +13,10 @@
 
 namespace gwtf {
 
+// hi = x rounded to tf32 (nearest, ties away) in two integer ops (cvt.rna.tf32.f32 compiles to five: it
+// also guards inf/nan, which the flow nets' O(1) operands never are); lo = x - hi is exact.
 __device__ __forceinline__ void split_tf32_bits(float x, uint32_t& hi, uint32_t& lo) {
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
+    hi = (__float_as_uint(x) + 0x1000u) & 0xffffe000u;
     lo = __float_as_uint(x - __uint_as_float(hi));
 }
 

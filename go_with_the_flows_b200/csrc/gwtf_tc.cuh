@@ -91,10 +91,11 @@ __device__ __forceinline__ void tmem_st(uint32_t a, const float (&s)[N]) {
 // ---------------------------------------------------------------------------------------------
 // 3xTF32 split
 // ---------------------------------------------------------------------------------------------
+// hi = x rounded to tf32 (nearest, ties away: add half an ulp of the 10-bit mantissa, clear the 13 low
+// bits) in two integer ops -- cvt.rna.tf32.f32 compiles to five (it also guards inf/nan, which the
+// O(1) activations and weights of the flow nets never are); lo = x - hi is exact.
 __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
-    uint32_t h;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
-    hi = __uint_as_float(h);
+    hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
     lo = x - hi;
 }
 

@@ -83,6 +83,10 @@ int gwtf_param_offsets(int32_t n_features, int32_t n_warp, int32_t* offsets, int
 
 /* Device-side FP32 FMA throughput probe used by bench.py for the roofline denominator. */
 int gwtf_fma_peak_tflops(int32_t iters, double* tflops, void* stream);
+/* Dense TF32 throughput of the warp-level tensor-core path (mma.sync.m16n8k8, register fragments) the
+ * backward kernels run on, measured by an issue-rate probe kernel; the 3xTF32 split executes three such
+ * MMAs per fp32-grade product. */
+int gwtf_mma_peak_tflops(int32_t iters, double* tflops, void* stream);
 
 /* ---- fused eval-mode forward NLL  (flow_mixture.py:163-166 + losses.py:88-137, BN running stats)
  * One launch walks all K stacks for every point, keeps xyz + log-det in registers, streams the
