@@ -44,6 +44,14 @@ CASES = {
     'small_fixed_learned': (dict(n_components=4, params_reduce_mode='none', weights_type='learned_weights',
                                  p_decoder_n_flows=1, p_decoder_n_features=5, g_latent_space_size=8,
                                  p_decoder_base_type='fixed'), 2, 64),
+    # feature widths beyond the tcgen05 tile budget (F > 39: the mma.sync engine, padded to 48) and an odd
+    # width padded to 32
+    'small_wide_learned': (dict(n_components=2, params_reduce_mode='none', weights_type='learned_weights',
+                                p_decoder_n_flows=1, p_decoder_n_features=44, g_latent_space_size=16,
+                                p_decoder_base_type='free'), 2, 40),
+    'small_mid_global': (dict(n_components=3, params_reduce_mode='none', weights_type='global_weights',
+                              p_decoder_n_flows=1, p_decoder_n_features=27, g_latent_space_size=8,
+                              p_decoder_base_type='freevar'), 3, 37),
 }
 
 
@@ -154,7 +162,10 @@ def to_np(d, prefix):
 
 
 def main():
+    only = set(sys.argv[1:])          # optional: regenerate just the named cases (seeds depend on the case index)
     for ci, (name, (ov, B, N)) in enumerate(CASES.items()):
+        if only and name not in only:
+            continue
         cfg, model = build(ov, 100 + ci)
         gen = torch.Generator().manual_seed(7 + ci)
         G = cfg['g_latent_space_size']
