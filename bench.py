@@ -359,7 +359,7 @@ def main():
     barrier()
 
     sampler = ClockSampler(local_rank)
-    if rank == 0:
+    if rank == 0 and os.environ.get('GWTF_BENCH_NO_SAMPLER') != '1':
         sampler.start()
     # ---- device-resident timing: K steps, each bracketed by CUDA events, L2 flushed in between
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]

@@ -13,6 +13,7 @@
 #include "gwtf_bwd_mma.cuh"
 #include "gwtf_fwd_mma.cuh"
 #include "gwtf_sample.cuh"
+#include "gwtf_exchange.cuh"
 
 using namespace gwtf;
 
@@ -68,6 +69,25 @@ bool use_tc(int F) { const int m = fwd_engine(F); return m == 1 || m == 2; }
 bool use_mma_fwd(int F) { return fwd_engine(F) == 3; }
 // backward contractions on mma.sync register fragments (any F <= 64) unless the FMA engine is selected
 bool use_mma_bwd() { tc_mode(1); return g_use_tc != 0; }
+
+// peer-memory statistic exchange of this process (gwtf_exchange_attach)
+struct ExchangeCtx {
+    int rank = 0, world = 1, slot = 0;
+    unsigned long long seq = 0;
+    double* recv[kMaxRanks] = {};
+    unsigned long long* flags[kMaxRanks] = {};
+} g_xchg;
+
+int exchange_sum(double* data, int n, cudaStream_t st) {
+    if (g_xchg.world <= 1) return 0;
+    if (n > g_xchg.slot) return fail(-20, "exchange slot too small for this stack");
+    ExchangeArgs a;
+    a.rank = g_xchg.rank; a.world = g_xchg.world; a.n = n; a.slot = g_xchg.slot; a.seq = ++g_xchg.seq; a.data = data;
+    for (int r = 0; r < kMaxRanks; ++r) { a.recv[r] = g_xchg.recv[r]; a.flags[r] = g_xchg.flags[r]; }
+    k_exchange_sum<<<1, 256, 0, st>>>(a);
+    GWTF_CUDA(cudaGetLastError());
+    return 0;
+}
 
 int padded_features(int F) {
     const int opts[] = {8, 16, 24, 32, 36, 40, 48, 64};
@@ -381,16 +401,38 @@ int gwtf_nll_from_state(const gwtf_stack_desc* desc, const float* ubuf, const fl
     return 0;
 }
 
-int gwtf_fwd_all(const gwtf_stack_desc* desc, int32_t train, const float* params, const float* bnbuf,
-                 const float* film, const float* points, const float* base, const float* logw, float* ubuf, float* ld,
-                 float* ssum, float* ybuf, double* mom, double* sum1, float* bstat, int32_t B, int32_t N, float* nll,
-                 float* logp, void* stream) {
+int gwtf_exchange_attach(int32_t rank, int32_t world, void* const* recv, void* const* flags, int32_t slot_doubles) {
+    if (world < 1 || world > kMaxRanks || rank < 0 || rank >= world) return fail(-21, "bad rank / world size");
+    if (world > 1 && (!recv || !flags || slot_doubles <= 0)) return fail(-21, "exchange buffers missing");
+    g_xchg = ExchangeCtx();
+    g_xchg.rank = rank; g_xchg.world = world; g_xchg.slot = slot_doubles;
+    for (int r = 0; r < world && world > 1; ++r) {
+        if (!recv[r] || !flags[r]) return fail(-21, "null peer pointer");
+        g_xchg.recv[r] = (double*)recv[r];
+        g_xchg.flags[r] = (unsigned long long*)flags[r];
+    }
+    return 0;
+}
+int gwtf_exchange_world(void) { return g_xchg.world; }
+int gwtf_exchange_sum(double* data, int32_t n, void* stream) {
+    if (!data || n <= 0) return fail(-10, "null pointer argument");
+    return exchange_sum(data, n, (cudaStream_t)stream);
+}
+
+// n_total > 0: statistics are over n_total points on all ranks; the sums are exchanged between phases
+// through the attached peer-memory exchange
+static int fwd_all_impl(const gwtf_stack_desc* desc, int32_t train, const float* params, const float* bnbuf,
+                        const float* film, const float* points, const float* base, const float* logw, float* ubuf,
+                        float* ld, float* ssum, float* ybuf, double* mom, double* sum1, float* bstat, int32_t B,
+                        int32_t N, float* nll, float* logp, double n_total_in, void* stream) {
     if (int rc = check_desc(desc)) return rc;
     if (!ubuf || !ld) return fail(-10, "null pointer argument");
     if (B <= 0 || N <= 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
     const int L = desc->n_layers, K = desc->n_components, F = desc->n_features;
-    const double n_total = (double)B * (double)N;
+    const bool ranks = n_total_in > 0.0 && train;
+    if (ranks && g_xchg.world <= 1) return fail(-22, "gwtf_exchange_attach has not been called");
+    const double n_total = n_total_in > 0.0 ? n_total_in : (double)B * (double)N;
     GWTF_CUDA(cudaMemsetAsync(ld, 0, sizeof(float) * (size_t)K * B * N, st));
     if (ssum) GWTF_CUDA(cudaMemsetAsync(ssum, 0, sizeof(float) * (size_t)K * B * 3 * N, st));
     if (train) {
@@ -400,9 +442,12 @@ int gwtf_fwd_all(const gwtf_stack_desc* desc, int32_t train, const float* params
         if (int rc = gwtf_fwd_moments(desc, points, B, N, mom + (size_t)(L - 1) * K * GWTF_MOM_STRIDE, stream)) return rc;
     }
     for (int l = L - 1; l >= 0; --l) {
-        if (train)
+        if (train) {
+            if (ranks) if (int rc = exchange_sum(mom + (size_t)l * K * GWTF_MOM_STRIDE, K * GWTF_MOM_STRIDE, st)) return rc;
             if (int rc = gwtf_fwd_layer(desc, l, 0, 1, params, bnbuf, film, points, ubuf, ld, ssum, ybuf, mom, sum1, B,
                                         N, n_total, stream)) return rc;
+            if (ranks) if (int rc = exchange_sum(sum1 + (size_t)l * K * 4 * F, K * 4 * F, st)) return rc;
+        }
         if (int rc = gwtf_fwd_layer(desc, l, 1, train, params, bnbuf, film, points, ubuf, ld, ssum, ybuf, mom, sum1, B,
                                     N, n_total, stream)) return rc;
     }
@@ -410,6 +455,22 @@ int gwtf_fwd_all(const gwtf_stack_desc* desc, int32_t train, const float* params
         if (int rc = gwtf_fwd_bstat(desc, params, mom, sum1, n_total, bstat, stream)) return rc;
     if (nll) return gwtf_nll_from_state(desc, ubuf, ld, base, logw, B, N, nll, logp, stream);
     return 0;
+}
+
+int gwtf_fwd_all(const gwtf_stack_desc* desc, int32_t train, const float* params, const float* bnbuf,
+                 const float* film, const float* points, const float* base, const float* logw, float* ubuf, float* ld,
+                 float* ssum, float* ybuf, double* mom, double* sum1, float* bstat, int32_t B, int32_t N, float* nll,
+                 float* logp, void* stream) {
+    return fwd_all_impl(desc, train, params, bnbuf, film, points, base, logw, ubuf, ld, ssum, ybuf, mom, sum1, bstat, B, N,
+                        nll, logp, 0.0, stream);
+}
+int gwtf_fwd_all_ranks(const gwtf_stack_desc* desc, int32_t train, const float* params, const float* bnbuf,
+                       const float* film, const float* points, const float* base, const float* logw, float* ubuf,
+                       float* ld, float* ssum, float* ybuf, double* mom, double* sum1, float* bstat, int32_t B,
+                       int32_t N, float* nll, float* logp, double n_total, void* stream) {
+    if (!(n_total > 0.0)) return fail(-23, "n_total must be the number of points on all ranks");
+    return fwd_all_impl(desc, train, params, bnbuf, film, points, base, logw, ubuf, ld, ssum, ybuf, mom, sum1, bstat, B, N,
+                        nll, logp, n_total, stream);
 }
 
 #include "gwtf_api_bwd.inc"

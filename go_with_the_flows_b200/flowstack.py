@@ -38,6 +38,49 @@ def _world():
     return 1
 
 
+_PEER = {'state': None, 'keep': None}     # process-wide peer-memory statistic exchange (see gwtf.h)
+
+
+def peer_exchange(slot_doubles, dev):
+    """Attach the NVLink peer-memory statistic exchange (csrc/gwtf_exchange.cuh) once per process: a
+    symmetric-memory buffer per rank holding the flag array and the double-buffered receive slots.
+    Returns True when the exchange is usable, False when the ranks should fall back to NCCL all-reduces
+    of the statistic arrays (CPU/gloo groups, GWTF_PEER_EXCHANGE=0, no symmetric memory)."""
+    import os
+    st = _PEER['state']
+    if st is not None and (st is False or st >= slot_doubles):
+        return bool(st)
+    if os.environ.get('GWTF_PEER_EXCHANGE', '1') == '0' or dist.get_backend() != 'nccl':
+        _PEER['state'] = False
+        return False
+    world, rank = dist.get_world_size(), dist.get_rank()
+    ok = torch.ones(1, device=dev)
+    try:
+        import torch.distributed._symmetric_memory as symm
+        slot = max(int(slot_doubles), 2048)
+        head = 32                                   # doubles reserved for the flag array (>= world uint64)
+        buf = symm.empty(head + 2 * world * slot, dtype=torch.float64, device=dev)
+        buf.zero_()
+        hdl = symm.rendezvous(buf, dist.group.WORLD)
+        ptrs = [int(q) for q in hdl.buffer_ptrs]
+        torch.cuda.synchronize(dev)
+        hdl.barrier()
+    except Exception:                               # any rank failing means every rank falls back
+        ok.zero_()
+        ptrs = None
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    if float(ok.item()) < 1.0:
+        _PEER['state'] = False
+        return False
+    arr = ctypes.c_void_p * world
+    recv = arr(*[ctypes.c_void_p(q + head * 8) for q in ptrs])
+    flags = arr(*[ctypes.c_void_p(q) for q in ptrs])
+    nat.check(nat.lib().gwtf_exchange_attach(rank, world, recv, flags, slot), 'gwtf_exchange_attach')
+    _PEER['state'] = slot
+    _PEER['keep'] = (buf, hdl)
+    return True
+
+
 class _LayerRef:
     """Direct references to the tensors of one coupling layer, in record order."""
     __slots__ = ('module', 'warp', 'point', 'cond', 'bn_point')
@@ -70,7 +113,7 @@ class _Master:
         self.tensor = None
         self.members = []      # (owner module, attribute name, is_param, offset, shape)
         self.grad_views = None
-        self.grad_ptr = None
+        self.grad_buf = None   # persistent gradient storage the per-parameter .grad views point into
         self.params = None     # Parameter objects of the members (grad masters only)
 
     def add(self, owner, attr, is_param, offset, shape):
@@ -239,6 +282,7 @@ class FlowStack:
                 flat.register_post_accumulate_grad_hook(self._make_attach_hook(ms))
             ms.tensor = flat
             ms.grad_views = None
+            ms.grad_buf = None
 
     def _make_reduce_hook(self):
         def hook(grad):
@@ -255,15 +299,23 @@ class FlowStack:
         return hook
 
     def _attach_grads(self, ms):
+        """Give every module Parameter of a master its `.grad` as a view of the master's gradient.  The
+        gradient lives in a persistent buffer (autograd hands over a fresh tensor after every
+        `zero_grad(set_to_none=True)`; it is copied in), so the ~4,000 views are built once and a step only
+        re-assigns them when the caller dropped the parameters' .grad."""
         g = ms.tensor.grad
         if g is None:
             return
-        if ms.grad_views is None or ms.grad_ptr != g.data_ptr():
-            gv = g.view(-1)
+        buf = ms.grad_buf
+        if buf is None or buf.shape != g.shape or buf.device != g.device or buf.dtype != g.dtype:
+            buf = ms.grad_buf = torch.empty_like(g, memory_format=torch.contiguous_format)
+            gv = buf.view(-1)
             ms.grad_views = [gv[m[3]:m[3] + _numel(m[4])].view(m[4]) for m in ms.members]
-            ms.grad_ptr = g.data_ptr()
+        if g.data_ptr() != buf.data_ptr():
+            buf.copy_(g)
+            ms.tensor.grad = buf
         sentinel = ms.params[0]
-        if sentinel.grad is None or sentinel.grad.data_ptr() != g.data_ptr() + ms.members[0][3] * 4:
+        if sentinel.grad is None or sentinel.grad.data_ptr() != buf.data_ptr() + ms.members[0][3] * buf.element_size():
             for prm, v in zip(ms.params, ms.grad_views):
                 prm.grad = v
 
@@ -292,8 +344,7 @@ class FlowStack:
         for name in self.grad_masters:
             ms = self.masters[name]
             if ms.tensor.grad is not None and ms.current(ms.members[0]).grad is None:
-                ms.tensor.grad = None
-                ms.grad_views = None
+                ms.tensor.grad = None      # (the persistent buffer and its views are kept)
 
     def global_points(self, B, N, dev):
         """Number of points the SyncBN statistics run over (sum of B*N over ranks).  The all-reduced
@@ -512,10 +563,18 @@ class _StackNLLPass(torch.autograd.Function):
             mom = torch.zeros(L, K, nat.MOM_STRIDE, device=dev, dtype=torch.float64)
             sum1 = torch.zeros(L, K, 2, 2, Fd, device=dev, dtype=torch.float64)
             bstat = torch.empty(L, K, 2, 4, Fd, device=dev)
+        peer = sync and peer_exchange(K * 8 * Fd, dev)
         if not sync:
             nat.check(lib.gwtf_fwd_all(desc, int(training), nat.ptr(params), nat.ptr(bnbuf), nat.ptr(film), nat.ptr(p),
                                        None, None, nat.ptr(ubuf), nat.ptr(ld), nat.ptr(ssum), nat.ptr(ybuf), nat.ptr(mom),
                                        nat.ptr(sum1), nat.ptr(bstat), B, N, None, None, st), 'gwtf_fwd_all')
+        elif peer:
+            # one call: the statistic sums cross ranks through NVLink peer memory between the kernel phases
+            n_total = stack.global_points(B, N, dev)
+            nat.check(lib.gwtf_fwd_all_ranks(desc, 1, nat.ptr(params), nat.ptr(bnbuf), nat.ptr(film), nat.ptr(p),
+                                             None, None, nat.ptr(ubuf), nat.ptr(ld), nat.ptr(ssum), nat.ptr(ybuf),
+                                             nat.ptr(mom), nat.ptr(sum1), nat.ptr(bstat), B, N, None, None, n_total, st),
+                      'gwtf_fwd_all_ranks')
         else:
             n_total = stack.global_points(B, N, dev)
             nat.check(lib.gwtf_fwd_moments(desc, nat.ptr(p), B, N, nat.ptr(mom[L - 1]), st), 'gwtf_fwd_moments')
@@ -532,6 +591,7 @@ class _StackNLLPass(torch.autograd.Function):
         ctx.stack = stack
         ctx.training = training
         ctx.sync = sync
+        ctx.peer = bool(peer)
         ctx.n_total = n_total
         # running stats are updated in place right after a train-mode forward (and are not read by
         # the train-mode backward), so they must not go through save_for_backward's version check
@@ -567,6 +627,12 @@ class _StackNLLPass(torch.autograd.Function):
                                        None, None, nat.ptr(ubuf), nat.ptr(ybuf), None, nat.ptr(mom), nat.ptr(sum1), None, None,
                                        nat.ptr(bsum), nat.ptr(gbuf), nat.ptr(gs), nat.ptr(dobuf), nat.ptr(dparams),
                                        nat.ptr(dfilm), None, None, nat.ptr(dpoints), B, N, st), 'gwtf_bwd_all')
+        elif ctx.peer:
+            nat.check(lib.gwtf_bwd_all_ranks(desc, train, nat.ptr(params), nat.ptr(bnbuf), nat.ptr(film), nat.ptr(p),
+                                             None, None, nat.ptr(ubuf), nat.ptr(ybuf), None, nat.ptr(mom), nat.ptr(sum1),
+                                             None, None, nat.ptr(bsum), nat.ptr(gbuf), nat.ptr(gs), nat.ptr(dobuf),
+                                             nat.ptr(dparams), nat.ptr(dfilm), None, None, nat.ptr(dpoints), B, N,
+                                             ctx.n_total, st), 'gwtf_bwd_all_ranks')
         else:
             for l in range(L):
                 for phase in (0, 1):

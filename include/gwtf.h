@@ -162,6 +162,30 @@ int gwtf_bwd_all(const gwtf_stack_desc* desc, int32_t train, const float* params
                  float* dobuf, float* dparams, float* dfilm, float* dbase, float* dlogw,
                  float* dpoints, int32_t B, int32_t N, void* stream);
 
+/* ---- several ranks (one process per GPU) sharing batch statistics: SyncBatchNorm semantics of the
+ * reference's DistributedDataParallel training (train_ae.py:77-78, torch.nn.SyncBatchNorm.convert_sync_batchnorm)
+ * The statistic sums of every layer phase are exchanged through NVLink peer memory by a push / flag /
+ * add kernel (csrc/gwtf_exchange.cuh) instead of a collective call per phase.
+ * gwtf_exchange_attach : recv[r] / flags[r] = device pointers, valid on THIS device, to rank r's receive
+ *                        buffer (2*world*slot_doubles doubles) and flag array (world uint64, zeroed before the
+ *                        first exchange and never written by the host afterwards); symmetric / IPC memory.
+ *                        world = 1 detaches.  All ranks must issue the same sequence of exchanges.
+ * gwtf_exchange_sum    : in-place sum over ranks of n <= slot_doubles doubles (stream ordered).
+ * gwtf_fwd_all_ranks / gwtf_bwd_all_ranks : the single-call drivers with n_total = points on all ranks. */
+int gwtf_exchange_attach(int32_t rank, int32_t world, void* const* recv, void* const* flags, int32_t slot_doubles);
+int gwtf_exchange_world(void);
+int gwtf_exchange_sum(double* data, int32_t n, void* stream);
+int gwtf_fwd_all_ranks(const gwtf_stack_desc* desc, int32_t train, const float* params, const float* bnbuf,
+                       const float* film, const float* points, const float* base, const float* logw,
+                       float* ubuf, float* ld, float* ssum, float* ybuf, double* mom, double* sum1, float* bstat,
+                       int32_t B, int32_t N, float* nll, float* logp, double n_total, void* stream);
+int gwtf_bwd_all_ranks(const gwtf_stack_desc* desc, int32_t train, const float* params, const float* bnbuf,
+                       const float* film, const float* points, const float* base, const float* logw,
+                       const float* ubuf, const float* ybuf, const float* ld, const double* mom, const double* sum1,
+                       const float* nll, const float* dnll, double* bsum, float* gbuf, float* gs,
+                       float* dobuf, float* dparams, float* dfilm, float* dbase, float* dlogw,
+                       float* dpoints, int32_t B, int32_t N, double n_total, void* stream);
+
 /* ---- sampling (flow_mixture.py:141-177 + models.py:199-203, eval-mode BN, lifted to a batch)
  * Per point: Philox4x32-10 counter (n, b, call, 0), key (seed lo32, stream ^ seed hi32) -> u -> component via
  * cdf (B,K) with np.searchsorted(side='right'); Box-Muller noise -> z = mu_base +
