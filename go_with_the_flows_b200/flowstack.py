@@ -48,6 +48,9 @@ def peer_exchange(slot_doubles, dev):
     of the statistic arrays (CPU/gloo groups, GWTF_PEER_EXCHANGE=0, no symmetric memory)."""
     import os
     st = _PEER['state']
+    if _PEER.get('group') != (dist.get_world_size(), dist.get_rank()):
+        st = _PEER['state'] = None                  # a new process group: attach again
+        _PEER['group'] = (dist.get_world_size(), dist.get_rank())
     if st is not None and (st is False or st >= slot_doubles):
         return bool(st)
     if os.environ.get('GWTF_PEER_EXCHANGE', '1') == '0' or dist.get_backend() != 'nccl':
