@@ -248,6 +248,11 @@ def kernel_only_times(model, p, g, reps, keep=None):
     return out
 
 
+def nat_engine():
+    from go_with_the_flows_b200 import _native as nat
+    return int(nat.lib().gwtf_engine())
+
+
 def side_workloads(model, cfg, dev, N):
     """Other hot-path entry points (not the headline): fused eval-mode NLL (BASELINE configs[0] shape
     at 64 clouds) and sampling (configs[3]/[4] shape: 256 latents x N points).  CUDA-event timed."""
@@ -274,7 +279,7 @@ def side_workloads(model, cfg, dev, N):
 
             ms = timed(lambda: model.decode(p, g, N))
             out['eval_nll_fused'] = {'points_per_s': 64 * N / (ms * 1e-3), 'ms': ms, 'clouds': 64, 'points': N,
-                                     'kernel': 'k_nll_eval (one launch, fp32 FMA)'}
+                                     'kernel': 'per-layer tensor-core kernels, eval-mode BN (gwtf_nll_fwd_eval_layers)' if nat_engine() != 0 else 'k_nll_eval (one launch, fp32 FMA)'}
             _, g2 = synthetic(256, N, G, seed_shift=9)
             g2 = g2.to(dev)
             stack = model.flow_stack()

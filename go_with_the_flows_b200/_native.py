@@ -30,6 +30,7 @@ _SIGNATURES = {
     'gwtf_fma_peak_tflops': [c_i, ctypes.POINTER(c_d), c_f],
     'gwtf_mma_peak_tflops': [c_i, ctypes.POINTER(c_d), c_f],
     'gwtf_nll_fwd_eval': [_D, c_f, c_f, c_f, c_f, c_f, c_f, c_i, c_i, c_f, c_f, c_f, c_f, c_f],
+    'gwtf_nll_fwd_eval_layers': [_D] + [c_f] * 8 + [c_i, c_i, c_f, c_f, c_f],
     'gwtf_fwd_moments': [_D, c_f, c_i, c_i, c_f, c_f],
     'gwtf_fwd_layer': [_D, c_i, c_i, c_i] + [c_f] * 10 + [c_i, c_i, c_d, c_f],
     'gwtf_fwd_layer_ex': [_D, c_i, c_i, c_i, c_i, c_f, c_f, c_f, c_f, c_i] + [c_f] * 8 + [c_i, c_i, c_d, c_f],

@@ -401,6 +401,31 @@ int gwtf_nll_from_state(const gwtf_stack_desc* desc, const float* ubuf, const fl
     return 0;
 }
 
+// Eval-mode NLL through the per-layer kernels of the current engine (tensor cores): L launches that ping-pong
+// between two (K,B,3,N) slots of `scratch`, then the mixture head.  Faster than the single-launch FMA kernel
+// at every size measured on B200 (64 x 2048: 2.2 vs 3.3 ms; 4 x 2048: 0.5 vs 3.3 ms).
+int gwtf_nll_fwd_eval_layers(const gwtf_stack_desc* desc, const float* params, const float* bnbuf, const float* film,
+                             const float* points, const float* base, const float* logw, float* scratch, float* ld,
+                             int32_t B, int32_t N, float* nll, float* logp, void* stream) {
+    if (int rc = check_desc(desc)) return rc;
+    if (!params || !bnbuf || !film || !points || !base || !logw || !scratch || !ld || !nll)
+        return fail(-10, "null pointer argument");
+    if (B <= 0 || N <= 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int L = desc->n_layers, K = desc->n_components;
+    const size_t slot = (size_t)K * B * 3 * N;
+    GWTF_CUDA(cudaMemsetAsync(ld, 0, sizeof(float) * (size_t)K * B * N, st));
+    const float* xin = points;
+    for (int l = L - 1; l >= 0; --l) {
+        float* xout = scratch + (size_t)(l & 1) * slot;
+        if (int rc = gwtf_fwd_layer_ex(desc, l, 1, 0, 0, params, bnbuf, film, xin, l == L - 1 ? 1 : 0, xout, ld, nullptr,
+                                       nullptr, nullptr, nullptr, nullptr, nullptr, B, N, (double)B * (double)N, stream))
+            return rc;
+        xin = xout;
+    }
+    return gwtf_nll_from_state(desc, scratch, ld, base, logw, B, N, nll, logp, stream);
+}
+
 int gwtf_exchange_attach(int32_t rank, int32_t world, void* const* recv, void* const* flags, int32_t slot_doubles) {
     if (world < 1 || world > kMaxRanks || rank < 0 || rank >= world) return fail(-21, "bad rank / world size");
     if (world > 1 && (!recv || !flags || slot_doubles <= 0)) return fail(-21, "exchange buffers missing");

@@ -472,6 +472,17 @@ class FlowStack:
         B, _, N = p.shape
         nll = torch.empty(B, N, device=p.device)
         logp = torch.empty(B, N, self.K, device=p.device) if want_logp else None
+        if nat.lib().gwtf_engine() != 0:
+            # per-layer tensor-core kernels (L launches, two ping-pong slots): faster than the single-launch
+            # FMA kernel at every size measured (64 x 2048: 2.2 vs 3.3 ms; 4 x 2048: 0.5 vs 3.3 ms)
+            scratch = torch.empty(2, self.K, B, 3, N, device=p.device)
+            ld = torch.empty(self.K, B, N, device=p.device)
+            nat.check(nat.lib().gwtf_nll_fwd_eval_layers(ctypes.byref(self.desc), nat.ptr(params), nat.ptr(bnbuf),
+                                                         nat.ptr(film), nat.ptr(p), nat.ptr(base.contiguous()),
+                                                         nat.ptr(logw.contiguous()), nat.ptr(scratch), nat.ptr(ld), B, N,
+                                                         nat.ptr(nll), nat.ptr(logp), _stream_ptr()),
+                      'gwtf_nll_fwd_eval_layers')
+            return (nll, logp) if want_logp else nll
         nat.check(nat.lib().gwtf_nll_fwd_eval(ctypes.byref(self.desc), nat.ptr(params), nat.ptr(bnbuf), nat.ptr(film),
                                               nat.ptr(p), nat.ptr(base.contiguous()), nat.ptr(logw.contiguous()),
                                               B, N, nat.ptr(nll), nat.ptr(logp), None, None, _stream_ptr()),

@@ -106,6 +106,11 @@ int gwtf_nll_fwd_eval(const gwtf_stack_desc* desc, const float* params, const fl
  *                    phase 1 is needed.  n_total = number of points the statistics are over
  *                    (B*N summed over ranks) -- the caller all-reduces mom/sum1 between phases.
  * gwtf_fwd_all     : single-process driver: moments + all layers + bstat + nll. */
+/* Eval-mode NLL (same result as gwtf_nll_fwd_eval) through the per-layer tensor-core kernels of the current
+ * engine: scratch = 2*K*B*3*N floats, ld = K*B*N floats (both overwritten). */
+int gwtf_nll_fwd_eval_layers(const gwtf_stack_desc* desc, const float* params, const float* bnbuf,
+                             const float* film, const float* points, const float* base, const float* logw,
+                             float* scratch, float* ld, int32_t B, int32_t N, float* nll, float* logp, void* stream);
 int gwtf_fwd_moments(const gwtf_stack_desc* desc, const float* points, int32_t B, int32_t N,
                      double* mom, void* stream);
 int gwtf_fwd_layer(const gwtf_stack_desc* desc, int32_t layer, int32_t phase, int32_t train,
