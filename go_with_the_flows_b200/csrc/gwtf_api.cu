@@ -70,6 +70,20 @@ bool use_mma_fwd(int F) { return fwd_engine(F) == 3; }
 // backward contractions on mma.sync register fragments (any F <= 64) unless the FMA engine is selected
 bool use_mma_bwd() { tc_mode(1); return g_use_tc != 0; }
 
+// launch with the programmatic-dependent-launch attribute (kernels that call pdl_wait() before touching
+// anything their predecessor wrote); GWTF_PDL=0 launches them the ordinary way
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    static const bool on = !(getenv("GWTF_PDL") && getenv("GWTF_PDL")[0] == '0');
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = on ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 // peer-memory statistic exchange of this process (gwtf_exchange_attach)
 struct ExchangeCtx {
     int rank = 0, world = 1, slot = 0;
@@ -84,8 +98,7 @@ int exchange_sum(double* data, int n, cudaStream_t st) {
     ExchangeArgs a;
     a.rank = g_xchg.rank; a.world = g_xchg.world; a.n = n; a.slot = g_xchg.slot; a.seq = ++g_xchg.seq; a.data = data;
     for (int r = 0; r < kMaxRanks; ++r) { a.recv[r] = g_xchg.recv[r]; a.flags[r] = g_xchg.flags[r]; }
-    k_exchange_sum<<<1, 256, 0, st>>>(a);
-    GWTF_CUDA(cudaGetLastError());
+    GWTF_CUDA(launch_pdl(k_exchange_sum, dim3(1), dim3(256), 0, st, a));
     return 0;
 }
 
@@ -206,8 +219,7 @@ int launch_fwd_layer_tcp(const LayerArgs& a0, cudaStream_t st) {
     int gx = num_sms() / K;                                  // one CTA per SM owns all 512 TMEM columns
     if (gx > (tiles + kSlots - 1) / kSlots) gx = (tiles + kSlots - 1) / kSlots;
     if (gx < 1) gx = 1;
-    kern<<<dim3(gx, K), kPersistThreads, smem, st>>>(a);
-    GWTF_CUDA(cudaGetLastError());
+    GWTF_CUDA(launch_pdl(kern, dim3(gx, K), dim3(kPersistThreads), smem, st, a));
     return 0;
 }
 

@@ -84,6 +84,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_bwd_layer_e_mma(const BwdArgs a
     src.sum1 = a.sum1 ? a.sum1 + (size_t)j * 4 * F : nullptr;
     src.n_total = a.n_total;
 
+    pdl_trigger();
     if (tid == 0) { mbar_init(&S.bar, 1); mbar_fence_init(); }
     if (warp == 0) tmem_alloc(&S.tmem_base, BwdETmem<FP>::alloc);
     tc_fence_before();
@@ -93,8 +94,10 @@ __global__ void __launch_bounds__(kThreads, 2) k_bwd_layer_e_mma(const BwdArgs a
     const uint32_t t_g = S.tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(warp >> 2) * (GC + EC);
     const uint32_t t_e = t_g + GC;
     mbar_wait(&S.bar, 0u);
-    stage_layer<FP, true>(S.W, &S.WB, raw, src, F, a.d.warp_mask[l], train, false,
-                          train ? a.bsum + (size_t)j * 8 * F : nullptr, tid, kThreads);
+    stage_w1t<FP>(S.W, raw, F, a.d.warp_mask[l], tid, kThreads);     // parameters only: may overlap phase 0's tail
+    pdl_wait();                                                       // phase 0 of this layer is complete from here on
+    stage_vectors<FP, true>(S.W, &S.WB, raw, src, F, a.d.warp_mask[l], train, false,
+                            train ? a.bsum + (size_t)j * 8 * F : nullptr, tid, kThreads);
 
     const unsigned wm = a.d.warp_mask[l];
     const int w = popc3(wm), k = 3 - w;
@@ -472,17 +475,20 @@ __global__ void __launch_bounds__(kThreads, 2) k_bwd_layer_d_mma(const BwdArgs a
     src.sum1 = a.sum1 ? a.sum1 + (size_t)j * 4 * F : nullptr;
     src.n_total = a.n_total;
 
+    pdl_trigger();
     if (tid == 0) { mbar_init(&S.bar, 1); mbar_fence_init(); }
     if (tid < 12) S.corr[tid] = 0.f;
     for (int i = tid; i < 2 * round_up(NV, 32); i += kThreads) (&S.red[0][0])[i] = 0.f;
     __syncthreads();
     if (tid == 0) issue_layer_copy(raw, src, F, !train, false, &S.bar);
+    mbar_wait(&S.bar, 0u);
+    if (!a.y1in) stage_w1t<FP>(S.W, raw, F, a.d.warp_mask[l], tid, kThreads);   // parameters only
+    pdl_wait();                                               // the previous layer's phase 1 is complete from here on
     const bool correct = train && a.mom_prev != nullptr;
     if (correct)
         bn0_correction<FP>(a.d, a.params, j, l - 1, a.mom_prev + j * GWTF_MOM_STRIDE, a.bsum_prev + (size_t)j * 8 * F,
                            a.n_total, S.corr, tid);
-    mbar_wait(&S.bar, 0u);
-    stage_layer<FP, true>(S.W, &S.WB, raw, src, F, a.d.warp_mask[l], train, false, nullptr, tid, kThreads);
+    stage_vectors<FP, true>(S.W, &S.WB, raw, src, F, a.d.warp_mask[l], train, false, nullptr, tid, kThreads);
     __syncthreads();
     float Mrow[3], ccd;
 #pragma unroll

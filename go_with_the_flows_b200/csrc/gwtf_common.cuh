@@ -202,13 +202,10 @@ __device__ __forceinline__ void stage_vectors(WT& W, WBT* WB, const float* raw, 
 // syncs before (raw complete) and after (W ready).
 //   train: BN statistics come from mom / sum1 (batch stats), else from the raw bn block.
 //   phase0: only q0 + W1T are needed (statistics pass).
-template <int FP, bool BWD>
-__device__ __forceinline__ void stage_layer(LayerW<FP>& W, LayerWB<FP>* WB, const float* raw, const LayerSrc& src,
-                                            int F, unsigned wmask, bool train, bool phase0, const double* bsum1,
-                                            int tid, int nthreads) {
-    stage_vectors<FP, BWD>(W, WB, raw, src, F, wmask, train, phase0, bsum1, tid, nthreads);
+// sd1 weight, transposed + zero padded (depends on the raw record only)
+template <int FP>
+__device__ __forceinline__ void stage_w1t(LayerW<FP>& W, const float* raw, int F, unsigned wmask, int tid, int nthreads) {
     const NetOffsets o = net_offsets(F, popc3(wmask));
-    // --- sd1 weight, transposed + zero padded
     for (int i = tid; i < 2 * FP * FP; i += nthreads) {
         const int net = i / (FP * FP), rem = i - net * FP * FP;
         const int f = rem / FP, e = rem - f * FP;   // read order: e fastest (coalesced in raw)
@@ -217,6 +214,20 @@ __device__ __forceinline__ void stage_layer(LayerW<FP>& W, LayerWB<FP>* WB, cons
         W.W1T[net][e][f] = v;
     }
 }
+template <int FP, bool BWD>
+__device__ __forceinline__ void stage_layer(LayerW<FP>& W, LayerWB<FP>* WB, const float* raw, const LayerSrc& src,
+                                            int F, unsigned wmask, bool train, bool phase0, const double* bsum1,
+                                            int tid, int nthreads) {
+    stage_vectors<FP, BWD>(W, WB, raw, src, F, wmask, train, phase0, bsum1, tid, nthreads);
+    stage_w1t<FP>(W, raw, F, wmask, tid, nthreads);
+}
+
+// Programmatic dependent launch (sm_90+): a kernel launched with the programmatic-serialization attribute
+// may start while its predecessor in the stream is still draining; everything it does before pdl_wait()
+// must depend on data older than the predecessor only (here: the parameter record and what is built from
+// it).  pdl_trigger() lets the NEXT kernel start launching.  Both are no-ops in an ordinary launch.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // FiLM fold for one shape: st = (s*istd1, t - s*mean1*istd1).  `film` = 4F floats (smem or global):
 // s_mu | t_mu | s_lv | t_lv.  Needs W.mi1 (stage_layer) to be visible.

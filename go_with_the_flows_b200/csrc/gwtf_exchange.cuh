@@ -27,6 +27,8 @@ struct ExchangeArgs {
 };
 
 __global__ void __launch_bounds__(256) k_exchange_sum(const ExchangeArgs a) {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the consumer's prologue may overlap the exchange
+    asm volatile("griddepcontrol.wait;" ::: "memory");                // the producer's sums are complete
     const int tid = threadIdx.x;
     const size_t par = (size_t)(a.seq & 1ull);
     for (int r = 0; r < a.world; ++r) {

@@ -88,6 +88,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) k_fwd_layer_tcp(const Laye
     src.sum1 = a.sum1 ? a.sum1 + (size_t)j * 4 * F : nullptr;
     src.n_total = a.n_total;
 
+    pdl_trigger();
     if (warp == kSlots * 4) tmem_alloc(&S.tmem_base, 512);
     if (tid == 0) {
         mbar_init(&S.bar_tma, 1);
@@ -100,15 +101,20 @@ __global__ void __launch_bounds__(kPersistThreads, 1) k_fwd_layer_tcp(const Laye
     __syncthreads();
     if (tid == 0) issue_layer_copy(raw, src, F, !train, false, &S.bar_tma);
     mbar_wait(&S.bar_tma, 0u);
+    const NetOffsets o = net_offsets(F, popc3(a.d.warp_mask[l]));
+    if (PHASE == 0) {                 // parameters only: may overlap the previous kernel's tail
+#pragma unroll
+        for (int net = 0; net < 2; ++net)
+            stage_b1<FPK, FPN>(S.ops[net], raw + net * o.stride + o.W1, nullptr, F, tid, kPersistThreads);
+    }
+    pdl_wait();                       // the statistics / points written by the previous kernel are complete from here on
     stage_vectors<FPN, false>(S.W, (LayerWB<FPN>*)nullptr, raw, src, F, a.d.warp_mask[l], train, PHASE == 0, nullptr,
                               tid, kPersistThreads);
     __syncthreads();
-    const NetOffsets o = net_offsets(F, popc3(a.d.warp_mask[l]));
 #pragma unroll
     for (int net = 0; net < 2; ++net) {
         stage_b0<FPK, FPN>(S.ops[net], S.W.q0[net], F, tid, kPersistThreads);
-        if (PHASE == 0) stage_b1<FPK, FPN>(S.ops[net], raw + net * o.stride + o.W1, nullptr, F, tid, kPersistThreads);
-        else stage_b2<FPK, FPN>(S.ops[net], S.W.w2[net], S.W.b2[net], F, tid, kPersistThreads);
+        if (PHASE != 0) stage_b2<FPK, FPN>(S.ops[net], S.W.w2[net], S.W.b2[net], F, tid, kPersistThreads);
     }
     fence_proxy_async();
     tc_fence_before();
