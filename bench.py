@@ -242,8 +242,12 @@ def kernel_only_times(model, p, g, reps, keep=None):
         return sum(best) / len(best)
 
     out = {'fwd_ms': timed(fwd), 'bwd_ms': timed(bwd), 'kept': bool(keep), 'kept_bytes': 4 * ybuf.numel() if keep else 0}
+    # one launch class at a time, ordinary launches: chaining a kernel behind ITSELF with programmatic dependent
+    # launch (which the real sequence never does) makes the early CTAs of launch n+1 compete with launch n
+    prev_pdl = lib.gwtf_set_pdl(0)
     for name, kind, phase in (('fwd_stats', 'fwd', 0), ('fwd_apply', 'fwd', 1), ('bwd_d', 'bwd', 0), ('bwd_e', 'bwd', 1)):
         out[name + '_ms_per_launch'] = timed(lambda: phase_loop(kind, phase)) / L
+    lib.gwtf_set_pdl(prev_pdl)
     del ybuf
     return out
 

@@ -25,6 +25,7 @@ _SIGNATURES = {
     'gwtf_version': [],
     'gwtf_set_tensor_cores': [c_i],
     'gwtf_engine': [],
+    'gwtf_set_pdl': [c_i],
     'gwtf_rec_stride': [c_i],
     'gwtf_param_offsets': [c_i, c_i, ctypes.POINTER(c_i), ctypes.POINTER(c_i)],
     'gwtf_fma_peak_tflops': [c_i, ctypes.POINTER(c_d), c_f],

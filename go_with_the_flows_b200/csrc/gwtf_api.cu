@@ -72,9 +72,11 @@ bool use_mma_bwd() { tc_mode(1); return g_use_tc != 0; }
 
 // launch with the programmatic-dependent-launch attribute (kernels that call pdl_wait() before touching
 // anything their predecessor wrote); GWTF_PDL=0 launches them the ordinary way
+int g_pdl = -1;        // programmatic dependent launch: -1 = from the environment (GWTF_PDL, default on)
 template <typename... KArgs, typename... Args>
 cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
-    static const bool on = !(getenv("GWTF_PDL") && getenv("GWTF_PDL")[0] == '0');
+    if (g_pdl < 0) g_pdl = (getenv("GWTF_PDL") && getenv("GWTF_PDL")[0] == '0') ? 0 : 1;
+    const bool on = g_pdl != 0;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
     cudaLaunchAttribute attr[1];
@@ -290,6 +292,11 @@ int gwtf_set_tensor_cores(int32_t enable) {
 }
 const char* gwtf_last_error_string(void) { return g_err; }
 
+int gwtf_set_pdl(int32_t enable) {
+    const int prev = g_pdl;
+    g_pdl = enable < 0 ? -1 : (enable ? 1 : 0);
+    return prev;
+}
 int gwtf_engine(void) { tc_mode(1); return g_use_tc; }
 
 int64_t gwtf_keep_floats(const gwtf_stack_desc* desc, int32_t B, int32_t N) {

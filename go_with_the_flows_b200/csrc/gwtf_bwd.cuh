@@ -126,6 +126,7 @@ struct BwdSmem {
     uint64_t bar;
     float corr[12];
     float red[2][round_up(5 * FP + 3, 32)];
+    uint32_t tmem_base;     // mma phase 0: tensor-memory accumulators
     float2 mif[2][FP];      // mma phase 0: n1 = v*mif.y - mif.x for the value v read/recomputed (h1 or kept y1)
 };
 

@@ -66,6 +66,9 @@ int gwtf_version(void);
  *   0 = FP32 FMA pipe everywhere;  -1 = re-read the GWTF_TC environment variable.
  * Returns the previous setting (NOT an error code). */
 int gwtf_set_tensor_cores(int32_t enable);
+/* Programmatic dependent launch of the layer kernels (their parameter staging overlaps the predecessor's
+ * tail): 1 = on (default), 0 = ordinary launches, -1 = re-read GWTF_PDL.  Returns the previous setting. */
+int gwtf_set_pdl(int32_t enable);
 /* The engine currently selected (0..3, environment resolved). */
 int gwtf_engine(void);
 /* Size in floats of the optional kept-activation buffer (`ybuf` of gwtf_fwd_layer / gwtf_fwd_all /
