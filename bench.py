@@ -448,7 +448,8 @@ def main():
                        'bn': 'train mode (batch statistics)', 'loss': loss_value},
             'e2e': {'value': e2e_value, 'unit': 'points/s', 'h2d_bytes_per_step': world * (p_host.numel() + g_host.numel()) * 4,
                     'd2h_bytes_per_step': world * 4, 'ms_per_step': e2e_ms / args.steps},
-            'gpu_launches': args.steps * (4 * L + 6),
+            # our kernels per step: 4 layer phases x L, moments/bstat/nll/seed/finish, + one exchange kernel per phase at N > 1
+            'gpu_launches': args.steps * (4 * L + 6 + (4 * L if world > 1 else 0)),
             'roofline': {'bound': 'tensor',
                          'kernel': 'k_bwd_layer_e_mma (dominant; per launch = one coupling layer, all K components)',
                          'achieved': dom['algorithmic_tflops'], 'peak': mma_peak.value / 3.0, 'unit': 'TFLOP/s',
