@@ -121,10 +121,12 @@ __global__ void __launch_bounds__(kThreads, 2) k_bwd_layer_e_mma(const BwdArgs a
             const int ln = i & 31, nt = (i >> 5) % NT, ks = (i >> 5) / NT;
             const int gg = ln >> 2, tt = ln & 3;
             uint32_t h0, l0, h1, l1;
-            // MMA #1: k = e (A columns t, t+4 <-> e = 8ks+2t, 8ks+2t+1), n = f = 8nt+g
-            split_tf32_bits(S.W.W1T[net][8 * ks + 2 * tt][8 * nt + gg], h0, l0);
-            split_tf32_bits(S.W.W1T[net][8 * ks + 2 * tt + 1][8 * nt + gg], h1, l1);
-            bf1[i] = make_float4(__uint_as_float(h0), __uint_as_float(h1), __uint_as_float(l0), __uint_as_float(l1));
+            // MMA #1: k = e (A columns t, t+4 <-> e = 8ks+2t, 8ks+2t+1), n = f = 8nt+g  (not needed when h1 is kept)
+            if (!a.y1in) {
+                split_tf32_bits(S.W.W1T[net][8 * ks + 2 * tt][8 * nt + gg], h0, l0);
+                split_tf32_bits(S.W.W1T[net][8 * ks + 2 * tt + 1][8 * nt + gg], h1, l1);
+                bf1[i] = make_float4(__uint_as_float(h0), __uint_as_float(h1), __uint_as_float(l0), __uint_as_float(l1));
+            }
             // MMA #2: k = f (8ks+2t, 8ks+2t+1), n = e = 8nt+g
             split_tf32_bits(S.W.W1T[net][8 * nt + gg][8 * ks + 2 * tt], h0, l0);
             split_tf32_bits(S.W.W1T[net][8 * nt + gg][8 * ks + 2 * tt + 1], h1, l1);
