@@ -142,10 +142,12 @@ __device__ __forceinline__ void issue_ss_k8(uint32_t d_tmem, const float* x_hi, 
 
 // all threads: relu the accumulator row of this thread and write it back as the next A operand
 // (all FPK columns are loaded in one go so the TMEM read latency is paid once, not per chunk)
-// base address of point (b, n) in the kept-activation buffer (gwtf_mma.cuh), or null
+// address of the (m-tile, row group) of point (b, n) in the kept-activation buffer (gwtf_mma.cuh), or null:
+// rows g and g+8 of an m-tile share it (their values interleave inside each 16-byte fragment element)
 __device__ __forceinline__ float* keep_ptr(float* keep, int j, int net, int F, int B, int N, int b, int n) {
     if (!keep) return nullptr;
-    return keep + keep_slab(F, B, N, j, net) + keep_point_base((size_t)b * keep_npad(N) + n, (F + 7) / 8);
+    const size_t p = (size_t)b * keep_npad(N) + n;
+    return keep + keep_slab(F, B, N, j, net) + ((p >> 4) * (size_t)(((F + 7) / 8) * 32) + (p & 7) * 4) * 4;
 }
 
 template <int FPK, int FPN>
@@ -155,14 +157,23 @@ __device__ __forceinline__ void relu_to_operand(uint32_t trow, float* keepf = nu
     tmem_ld<FPK>(trow + C::D, y);
     tmem_wait_ld();
     if (keepf) {
-        // y1 of this thread's point kept for the backward pass in MMA C-fragment order; rows beyond N hold zeros
+        // y1 kept for the backward pass in MMA C-fragment order: a 16-byte element = (row g: ch 2t, 2t+1 | row g+8:
+        // ch 2t, 2t+1).  This thread is one row; lanes l and l^8 are rows g and g+8 of the same m-tile, so they swap
+        // halves by shuffle and each writes whole elements (lane g: even channel pairs, lane g+8: odd pairs) --
+        // a warp store then fills complete 32-byte sectors.  Rows beyond N hold zeros.
+        const bool upper = (threadIdx.x & 8) != 0;
 #pragma unroll
-        for (int nt = 0; nt < FPK / 8; ++nt)
-            if (nt < keep_nt)
-#pragma unroll
-                for (int tt = 0; tt < 4; ++tt)
-                    *reinterpret_cast<float2*>(keepf + (nt * 32 + tt) * 4) =
-                        valid ? make_float2(y[8 * nt + 2 * tt], y[8 * nt + 2 * tt + 1]) : make_float2(0.f, 0.f);
+        for (int k = 0; k < FPK / 4; ++k) {
+            const int nt = k >> 1, t0 = (k & 1) * 2;
+            if (nt < keep_nt) {
+                const float e0 = valid ? y[8 * nt + 2 * t0] : 0.f, e1 = valid ? y[8 * nt + 2 * t0 + 1] : 0.f;
+                const float o0 = valid ? y[8 * nt + 2 * t0 + 2] : 0.f, o1 = valid ? y[8 * nt + 2 * t0 + 3] : 0.f;
+                const float r0 = __shfl_xor_sync(0xffffffffu, upper ? e0 : o0, 8);
+                const float r1 = __shfl_xor_sync(0xffffffffu, upper ? e1 : o1, 8);
+                const float4 out = upper ? make_float4(r0, r1, o0, o1) : make_float4(e0, e1, r0, r1);
+                *reinterpret_cast<float4*>(keepf + (nt * 32 + t0 + (upper ? 1 : 0)) * 4) = out;
+            }
+        }
     }
 #pragma unroll
     for (int c = 0; c < FPK; c += 8) {
