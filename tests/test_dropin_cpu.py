@@ -113,3 +113,32 @@ def test_flat_storage_survives_syncbn_conversion_and_zero_grad():
     assert torch.allclose(w.grad, g1)            # not accumulated on top of the stale master gradient
     stack.film(g, False, False).sum().backward()
     assert torch.allclose(w.grad, 2 * g1)        # but accumulated across backward calls like autograd does
+
+
+def test_cabi_host_side_queries_without_a_gpu():
+    """Entry points that only do host arithmetic / argument checks: engine selection, kept-activation
+    buffer size, exchange attachment validation (no kernel is launched)."""
+    import ctypes
+    from go_with_the_flows_b200 import _native as nat
+    lib = nat.lib()
+    prev = lib.gwtf_set_tensor_cores(2)
+    try:
+        assert lib.gwtf_engine() == 2
+        desc = nat.StackDesc()
+        desc.n_components, desc.n_layers, desc.n_features = 4, 33, 37
+        desc.rec_stride = lib.gwtf_rec_stride(37)
+        for l in range(33):
+            desc.warp_mask[l] = 1 << (l % 3)
+        # L * K * 2 nets * B * roundup256(N) * roundup8(F) floats under the tensor-core engines
+        assert lib.gwtf_keep_floats(ctypes.byref(desc), 64, 2048) == 33 * 4 * 2 * 64 * 2048 * 40
+        assert lib.gwtf_keep_floats(ctypes.byref(desc), 3, 50) == 33 * 4 * 2 * 3 * 256 * 40
+        lib.gwtf_set_tensor_cores(0)          # FMA engine: (L,K,2,F,B,N)
+        assert lib.gwtf_keep_floats(ctypes.byref(desc), 3, 50) == 33 * 4 * 2 * 37 * 3 * 50
+    finally:
+        lib.gwtf_set_tensor_cores(prev)
+    assert lib.gwtf_exchange_world() == 1
+    assert lib.gwtf_exchange_attach(0, 1, None, None, 0) == 0             # single rank: detach / no-op
+    assert lib.gwtf_exchange_attach(0, 4, None, None, 0) != 0             # several ranks need peer buffers
+    assert lib.gwtf_exchange_attach(5, 4, None, None, 0) != 0
+    assert lib.gwtf_exchange_world() == 1
+    assert lib.gwtf_set_pdl(lib.gwtf_set_pdl(1)) in (0, 1)
