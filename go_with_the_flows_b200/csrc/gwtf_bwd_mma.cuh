@@ -188,6 +188,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_bwd_layer_e_mma(const BwdArgs a
                 }
                 gold[r] = (valid[r] && t < 3) ? a.gbuf[sb + (size_t)t * N + n] : 0.f;
             }
+            const bool ragged = n0 + 16 > N;                  // some rows of this m-tile lie beyond the shape
             // ---- a0 (A fragments) and MMA #1: h1[row][f]  (or h1 kept by the forward pass)
             float h[NT][4];
             const bool kept = a.y1in != nullptr;
@@ -209,10 +210,12 @@ __global__ void __launch_bounds__(kThreads, 2) k_bwd_layer_e_mma(const BwdArgs a
                 av[3] = fmaf(qb.x, x[1][0], fmaf(qb.y, x[1][1], fmaf(qb.z, x[1][2], qb.w)));   // (row g+8, e1)
                 mask0 |= (av[0] > 0.f ? 1u : 0u) << (2 * ks) | (av[2] > 0.f ? 2u : 0u) << (2 * ks);
                 mask1 |= (av[1] > 0.f ? 1u : 0u) << (2 * ks) | (av[3] > 0.f ? 2u : 0u) << (2 * ks);
-                av[0] = valid[0] ? fmaxf(av[0], 0.f) : 0.f;
-                av[2] = valid[0] ? fmaxf(av[2], 0.f) : 0.f;
-                av[1] = valid[1] ? fmaxf(av[1], 0.f) : 0.f;
-                av[3] = valid[1] ? fmaxf(av[3], 0.f) : 0.f;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) av[i] = fmaxf(av[i], 0.f);
+                if (ragged) {                                   // warp-uniform: only the last tile of a shape
+                    if (!valid[0]) av[0] = av[2] = 0.f;
+                    if (!valid[1]) av[1] = av[3] = 0.f;
+                }
                 *reinterpret_cast<float2*>(Aw + g * FPS + 8 * ks + 2 * t) = make_float2(av[0], av[2]);
                 *reinterpret_cast<float2*>(Aw + (g + 8) * FPS + 8 * ks + 2 * t) = make_float2(av[1], av[3]);
                 if (!kept) {
@@ -243,7 +246,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_bwd_layer_e_mma(const BwdArgs a
                         const float y1 = fmaf(c1.x, hv, c1.y);
                         const float da = fmaf(c2.x, dO[r][0], fmaf(c2.y, dO[r][1], c2.z * dO[r][2]));
                         const float dh = (y1 > 0.f ? da : 0.f) + fmaf(hv, c1.z, c1.w);
-                        h[nt][2 * r + i] = valid[r] ? dh : 0.f;
+                        h[nt][2 * r + i] = (ragged && !valid[r]) ? 0.f : dh;
                     }
                 }
                 *reinterpret_cast<float2*>(Dw + g * FPS + 8 * nt + 2 * t) = make_float2(h[nt][0], h[nt][1]);
