@@ -291,7 +291,7 @@ def side_workloads(model, cfg, dev, N):
             mu_b, lv_b = model.base_gaussian(g2)
             ms = timed(lambda: sample_mixture(stack, g2, mu_b, lv_b, logits, N, 2026, 0))
             out['sampling'] = {'points_per_s': 256 * N / (ms * 1e-3), 'ms': ms, 'latents': 256, 'points': N,
-                               'kernel': 'k_sample (Philox draws + direct stacks, fp32 FMA)'}
+                               'kernel': 'Philox draws, points regrouped by component, per-layer tensor-core kernels in direct mode (gwtf_sample_layers)' if nat_engine() != 0 else 'k_sample (Philox draws + direct stacks, fp32 FMA)'}
     finally:
         model.train(was_training)
     return out

@@ -42,6 +42,9 @@ _SIGNATURES = {
     'gwtf_bwd_layer': [_D, c_i, c_i, c_i] + [c_f] * 14 + [c_i, c_i, c_d, c_f],
     'gwtf_bwd_finish': [_D, c_i, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_i, c_i, c_d, c_f],
     'gwtf_bwd_all': [_D, c_i] + [c_f] * 22 + [c_i, c_i, c_f],
+    'gwtf_sample_plan': [_D, c_f, c_i, c_i, ctypes.c_uint64, ctypes.c_uint32, c_f, c_f, c_f, c_f],
+    'gwtf_sample_layers': [_D, c_f, c_f, c_f, c_f, c_f, c_i, c_i, c_i, ctypes.c_uint64, ctypes.c_uint32, c_f, c_f, c_f,
+                           c_f, c_f, c_f, c_f, c_f],
     'gwtf_exchange_attach': [c_i, c_i, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_void_p), c_i],
     'gwtf_exchange_world': [],
     'gwtf_exchange_sum': [c_f, c_i, c_f],

@@ -222,3 +222,105 @@ __global__ void __launch_bounds__(kThreads) k_sample(const SampleArgs a) {
 }
 
 }  // namespace gwtf
+
+// =============================================================================================
+// Sampling through the per-layer tensor-core kernels.  The points of every shape are regrouped by
+// the component they drew -- (K, B, 3, Nmax) with Nmax = the largest per-(shape, component) count
+// rounded up to a tile -- pushed through the L direct layers with the same kernels the NLL passes
+// use (eval-mode BN, direct=1), and scattered back to their own slots.
+// =============================================================================================
+namespace gwtf {
+
+struct SamplePlanArgs {
+    int K, B, N;
+    const float* cdf;
+    uint32_t seed_lo, stream_id;
+    const int32_t* idx_in;
+    int32_t* counts;        // (B, K)
+    int32_t* nmax;          // running maximum over (b, j)
+};
+
+__device__ __forceinline__ int sample_component(const float* cdf, int K, const int32_t* idx_in, int b, int n, int N,
+                                                uint32_t seed_lo, uint32_t stream_id, uint4& w0) {
+    const uint2 key = make_uint2(seed_lo, stream_id);
+    w0 = philox4x32_10(make_uint4((uint32_t)n, (uint32_t)b, 0u, 0u), key);
+    int c = idx_in ? idx_in[(size_t)b * N + n] : pick_component(cdf, K, u01(w0.x));
+    return c < 0 ? 0 : (c >= K ? K - 1 : c);
+}
+
+// one CTA per shape: how many points drew each component
+__global__ void __launch_bounds__(kThreads) k_sample_count(const SamplePlanArgs a) {
+    __shared__ int cnt[GWTF_MAX_COMPONENTS];
+    const int b = blockIdx.x, tid = threadIdx.x;
+    if (tid < GWTF_MAX_COMPONENTS) cnt[tid] = 0;
+    __syncthreads();
+    const float* cdf = a.cdf + (size_t)b * a.K;
+    for (int n = tid; n < a.N; n += kThreads) {
+        uint4 w0;
+        atomicAdd(&cnt[sample_component(cdf, a.K, a.idx_in, b, n, a.N, a.seed_lo, a.stream_id, w0)], 1);
+    }
+    __syncthreads();
+    if (tid < a.K) {
+        a.counts[b * a.K + tid] = cnt[tid];
+        atomicMax(a.nmax, cnt[tid]);
+    }
+}
+
+struct SampleScatterArgs {
+    int K, B, N, Nmax;
+    const float *base, *cdf;
+    uint32_t seed_lo, stream_id;
+    const int32_t* idx_in;
+    const float* eps_in;
+    float* xbuf;            // (K, B, 3, Nmax) base-space samples grouped by component (padding pre-zeroed)
+    int32_t* slot;          // (B, N): j * Nmax + position
+    int32_t* labels;
+    float* z_out;
+};
+
+// one CTA per shape: draw, place every point in its component's segment (order inside a segment is free)
+__global__ void __launch_bounds__(kThreads) k_sample_scatter(const SampleScatterArgs a) {
+    __shared__ int cursor[GWTF_MAX_COMPONENTS];
+    const int b = blockIdx.x, tid = threadIdx.x, N = a.N, K = a.K;
+    if (tid < GWTF_MAX_COMPONENTS) cursor[tid] = 0;
+    __syncthreads();
+    float mub[3], sdb[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) { mub[d] = a.base[b * 6 + d]; sdb[d] = expf(0.5f * a.base[b * 6 + 3 + d]); }
+    const float* cdf = a.cdf + (size_t)b * K;
+    for (int n = tid; n < N; n += kThreads) {
+        uint4 w0;
+        const int c = sample_component(cdf, K, a.idx_in, b, n, N, a.seed_lo, a.stream_id, w0);
+        float e[3];
+        if (a.eps_in) {
+#pragma unroll
+            for (int d = 0; d < 3; ++d) e[d] = a.eps_in[((size_t)b * 3 + d) * N + n];
+        } else {
+            const uint4 w1 = philox4x32_10(make_uint4((uint32_t)n, (uint32_t)b, 1u, 0u), make_uint2(a.seed_lo, a.stream_id));
+            draw_normals(w0, w1, e);
+        }
+        const int pos = atomicAdd(&cursor[c], 1);
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            const float zv = fmaf(sdb[d], e[d], mub[d]);          // models.py:108: eps*std + mu
+            a.xbuf[(((size_t)c * a.B + b) * 3 + d) * a.Nmax + pos] = zv;
+            if (a.z_out) a.z_out[((size_t)b * 3 + d) * N + n] = zv;
+        }
+        a.slot[(size_t)b * N + n] = c * a.Nmax + pos;
+        a.labels[(size_t)b * N + n] = c + 1;                      // flow_mixture.py:176
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) k_sample_gather(int B, int N, int Nmax, const float* xbuf, const int32_t* slot,
+                                                            float* samples) {
+    const size_t total = (size_t)B * N;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int b = (int)(i / N), n = (int)(i - (size_t)b * N);
+        const int s = slot[i], j = s / Nmax, pos = s - j * Nmax;
+#pragma unroll
+        for (int d = 0; d < 3; ++d)
+            samples[((size_t)b * 3 + d) * N + n] = xbuf[(((size_t)j * B + b) * 3 + d) * Nmax + pos];
+    }
+}
+
+}  // namespace gwtf

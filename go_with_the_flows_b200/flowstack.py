@@ -759,6 +759,25 @@ def sample_mixture(stack, g, mu_base, lv_base, logits, n_points, seed, stream_id
         idx = idx.to(device=dev, dtype=torch.int32).contiguous()
     if eps is not None:
         eps = eps.to(device=dev, dtype=torch.float32).contiguous()
+    if lib.gwtf_engine() != 0:
+        # tensor-core engines: regroup the points by component and run the per-layer kernels in direct mode
+        # (needs the largest per-(shape, component) count on the host: one 4-byte read back)
+        K = stack.K
+        counts = torch.empty(B, K, device=dev, dtype=torch.int32)
+        nmax = torch.zeros(1, device=dev, dtype=torch.int32)
+        seed64, sid = ctypes.c_uint64(seed & (2 ** 64 - 1)), ctypes.c_uint32(stream_id & 0xFFFFFFFF)
+        nat.check(lib.gwtf_sample_plan(ctypes.byref(stack.desc), nat.ptr(cdf), B, n_points, seed64, sid, nat.ptr(idx),
+                                       nat.ptr(counts), nat.ptr(nmax), _stream_ptr()), 'gwtf_sample_plan')
+        nmax_pad = max(128, (int(nmax.item()) + 127) // 128 * 128)
+        if K * nmax_pad <= 3 * max(n_points, 128):      # very skewed mixtures: the fused kernel does less work
+            scratch = torch.empty(2 * K * B * 3 * nmax_pad, device=dev)
+            slot = torch.empty(B, n_points, device=dev, dtype=torch.int32)
+            nat.check(lib.gwtf_sample_layers(ctypes.byref(stack.desc), nat.ptr(params), nat.ptr(bnbuf), nat.ptr(film),
+                                             nat.ptr(base), nat.ptr(cdf), B, n_points, nmax_pad, seed64, sid,
+                                             nat.ptr(idx), nat.ptr(eps), nat.ptr(scratch), nat.ptr(slot),
+                                             nat.ptr(samples), nat.ptr(labels), nat.ptr(z), _stream_ptr()),
+                      'gwtf_sample_layers')
+            return samples, labels, z
     nat.check(lib.gwtf_sample(ctypes.byref(stack.desc), nat.ptr(params), nat.ptr(bnbuf), nat.ptr(film), nat.ptr(base),
                               nat.ptr(cdf), B, n_points, ctypes.c_uint64(seed & (2 ** 64 - 1)),
                               ctypes.c_uint32(stream_id & 0xFFFFFFFF), nat.ptr(idx), nat.ptr(eps), nat.ptr(samples),

@@ -204,6 +204,16 @@ int gwtf_sample(const gwtf_stack_desc* desc, const float* params, const float* b
                 const float* film, const float* base, const float* cdf, int32_t B, int32_t N,
                 uint64_t seed, uint32_t stream_id, const int32_t* idx_in, const float* eps_in,
                 float* samples, int32_t* labels, float* z_out, void* stream);
+/* The same sampling pass through the per-layer tensor-core kernels of the current engine: points regrouped by the
+ * component they drew.  gwtf_sample_plan counts the draws (counts (B,K) int32, *nmax = largest count; device
+ * memory); the caller reads *nmax back, rounds it up to a multiple of 128 (nmax_pad) and provides
+ * scratch = 2*K*B*3*nmax_pad floats and slot = B*N int32.  Results equal gwtf_sample's (same Philox streams). */
+int gwtf_sample_plan(const gwtf_stack_desc* desc, const float* cdf, int32_t B, int32_t N, uint64_t seed,
+                     uint32_t stream_id, const int32_t* idx_in, int32_t* counts, int32_t* nmax, void* stream);
+int gwtf_sample_layers(const gwtf_stack_desc* desc, const float* params, const float* bnbuf, const float* film,
+                       const float* base, const float* cdf, int32_t B, int32_t N, int32_t nmax_pad, uint64_t seed,
+                       uint32_t stream_id, const int32_t* idx_in, const float* eps_in, float* scratch, int32_t* slot,
+                       float* samples, int32_t* labels, float* z_out, void* stream);
 
 #ifdef __cplusplus
 }
