@@ -1,39 +1,45 @@
-// C ABI of libgwtf.so (see include/gwtf.h).  Host-side argument checks, template dispatch on
-// the padded feature width, launches on the caller's stream.  No allocation, no host sync.
-#include <cstdio>
-#include <cstdlib>
-#include <cstring>
-#include <cuda_runtime.h>
+// C ABI of libgwtf.so (see include/gwtf.h).  Host-side argument checks, engine dispatch, the single-call
+// drivers, the rank exchange, the fused AMSGrad step and the roofline probes.  Launches go on the caller's
+// stream; nothing here allocates device memory or synchronises the host (the two probes excepted), and there
+// is no mutable process-global state: options ride in the caller's gwtf_stack_desc.
+#include <new>
 
-#include "gwtf_common.cuh"
+#include "gwtf_host.h"
 #include "gwtf_fwd.cuh"
-#include "gwtf_tc_fwd.cuh"
-#include "gwtf_tc_persist.cuh"
 #include "gwtf_bwd.cuh"
-#include "gwtf_bwd_mma.cuh"
-#include "gwtf_fwd_mma.cuh"
 #include "gwtf_sample.cuh"
 #include "gwtf_exchange.cuh"
 
 using namespace gwtf;
 
+// peer-memory statistic exchange of one rank (gwtf_exchange_create)
+struct gwtf_exchange {
+    int rank = 0, world = 1, slot = 0;
+    unsigned long long seq = 0;
+    unsigned long long timeout_ns = 600ull * 1000000000ull;
+    double* recv[kMaxRanks] = {};
+    unsigned long long* flags[kMaxRanks] = {};
+};
+
+namespace gwtf {
+
+char* err_buf() {
+    static thread_local char buf[512] = "";
+    return buf;
+}
+
+size_t keep_layer_floats(const gwtf_stack_desc& d, int B, int N) {
+    const int F = d.n_features, K = d.n_components;
+    switch (bwd_engine(d)) {
+        case kEngineTc: return 0;                                        // the tcgen05 backward recomputes
+        case kEngineMma: return (size_t)K * mma_keep_floats(F, B, N);
+        default: return (size_t)K * 2 * F * B * N;
+    }
+}
+
+}  // namespace gwtf
+
 namespace {
-
-thread_local char g_err[512] = "";
-
-int fail(int code, const char* fmt, const char* what = "") {
-    snprintf(g_err, sizeof(g_err), fmt, what);
-    return code;
-}
-int cuda_fail(cudaError_t e, const char* where) {
-    snprintf(g_err, sizeof(g_err), "%s: %s", where, cudaGetErrorString(e));
-    return (int)e;
-}
-#define GWTF_CUDA(x)                                         \
-    do {                                                     \
-        cudaError_t e__ = (x);                               \
-        if (e__ != cudaSuccess) return cuda_fail(e__, #x);   \
-    } while (0)
 
 int check_desc(const gwtf_stack_desc* d) {
     if (!d) return fail(-1, "null stack descriptor");
@@ -45,263 +51,127 @@ int check_desc(const gwtf_stack_desc* d) {
         const int w = __builtin_popcount(d->warp_mask[l] & 7);
         if (w < 1 || w > 2 || (d->warp_mask[l] & ~7)) return fail(-6, "warp_mask must select 1 or 2 of the 3 dims");
     }
+    const int e = d->engine;
+    if (!(e == GWTF_ENGINE_DEFAULT || e == GWTF_ENGINE_FMA || e == GWTF_ENGINE_TC_FWD || e == GWTF_ENGINE_MMA ||
+          e == GWTF_ENGINE_TC))
+        return fail(-7, "unknown engine");
     return 0;
 }
 
-int g_use_tc = -1;    // -1: decide from the environment (GWTF_TC), 0 = FMA, 1 = tcgen05 (3 CTAs/SM),
-                      // 2 = tcgen05 persistent warp-specialised forward (1 CTA/SM, 4 tiles in flight; default),
-                      // 3 = warp-level mma.sync fragments for the forward too (the backward always uses them)
-
-int tc_mode(int F) {
-    if (g_use_tc < 0) {
-        const char* e = getenv("GWTF_TC");
-        g_use_tc = e ? (e[0] == '0' ? 0 : (e[0] == '1' ? 1 : (e[0] == '3' ? 3 : 2))) : 2;
-    }
-    return g_use_tc;
-}
-// forward engine for feature width F: the tcgen05 kernels need F + 1 <= 40, wider stacks take the mma.sync path
-int fwd_engine(int F) {
-    tc_mode(F);
-    if (g_use_tc == 0 || g_use_tc == 3) return g_use_tc;
-    return F <= 39 ? g_use_tc : 3;
-}
-bool use_tc(int F) { const int m = fwd_engine(F); return m == 1 || m == 2; }
-bool use_mma_fwd(int F) { return fwd_engine(F) == 3; }
-// backward contractions on mma.sync register fragments (any F <= 64) unless the FMA engine is selected
-bool use_mma_bwd() { tc_mode(1); return g_use_tc != 0; }
-
-// launch with the programmatic-dependent-launch attribute (kernels that call pdl_wait() before touching
-// anything their predecessor wrote); GWTF_PDL=0 launches them the ordinary way
-int g_pdl = -1;        // programmatic dependent launch: -1 = from the environment (GWTF_PDL, default on)
-template <typename... KArgs, typename... Args>
-cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
-    if (g_pdl < 0) g_pdl = (getenv("GWTF_PDL") && getenv("GWTF_PDL")[0] == '0') ? 0 : 1;
-    const bool on = g_pdl != 0;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr; cfg.numAttrs = on ? 1 : 0;
-    return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
-}
-
-// peer-memory statistic exchange of this process (gwtf_exchange_attach)
-struct ExchangeCtx {
-    int rank = 0, world = 1, slot = 0;
-    unsigned long long seq = 0;
-    double* recv[kMaxRanks] = {};
-    unsigned long long* flags[kMaxRanks] = {};
-} g_xchg;
-
-int exchange_sum(double* data, int n, cudaStream_t st) {
-    if (g_xchg.world <= 1) return 0;
-    if (n > g_xchg.slot) return fail(-20, "exchange slot too small for this stack");
+int exchange_sum(gwtf_exchange* x, double* data, int n, bool pdl, cudaStream_t st) {
+    if (!x || x->world <= 1) return 0;
+    if (n > x->slot) return fail(-20, "exchange slot too small for this stack");
     ExchangeArgs a;
-    a.rank = g_xchg.rank; a.world = g_xchg.world; a.n = n; a.slot = g_xchg.slot; a.seq = ++g_xchg.seq; a.data = data;
-    for (int r = 0; r < kMaxRanks; ++r) { a.recv[r] = g_xchg.recv[r]; a.flags[r] = g_xchg.flags[r]; }
-    GWTF_CUDA(launch_pdl(k_exchange_sum, dim3(1), dim3(256), 0, st, a));
+    a.rank = x->rank; a.world = x->world; a.n = n; a.slot = x->slot; a.seq = ++x->seq; a.data = data;
+    a.timeout_ns = x->timeout_ns;
+    for (int r = 0; r < kMaxRanks; ++r) { a.recv[r] = x->recv[r]; a.flags[r] = x->flags[r]; }
+    GWTF_CUDA(launch_pdl(pdl, k_exchange_sum, dim3(1), dim3(256), 0, st, a));
     return 0;
 }
 
-int padded_features(int F) {
-    const int opts[] = {8, 16, 24, 32, 36, 40, 48, 64};
-    for (int o : opts) if (F <= o) return o;
-    return -1;
-}
-
-int num_sms() {
-    static int sms = 0;
-    if (!sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+int fwd_layer_dispatch(const LayerArgs& a, int phase, cudaStream_t st) {
+    switch (fwd_engine(a.d)) {
+        case kEngineFma: return a.seg ? fail(-4, "segmented rows need the tcgen05 forward") : launch_fwd_layer_fma(a, phase, st);
+        case kEngineMma: return launch_fwd_layer_mma(a, phase, st);
+        default: return launch_fwd_layer_tc(a, phase, st);
     }
-    return sms;
-}
-
-template <typename KernelT>
-int blocks_per_sm(KernelT kernel, size_t smem) {
-    int n = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, kThreads, smem);
-    return n < 1 ? 1 : n;
-}
-
-template <typename KernelT>
-cudaError_t allow_smem(KernelT kernel, size_t smem) {
-    // ask for the full shared-memory carveout: the default preference sizes L1 vs shared from a
-    // heuristic and the occupancy query then reports 1 CTA/SM for 60-80 KB blocks
-    cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-}
-
-// points per thread for a padded width (register budget: P*FP accumulators)
-template <int FP> struct PointsPerThread { static constexpr int fwd = FP <= 40 ? 4 : 2; static constexpr int bwd = FP <= 40 ? 2 : 1; };
-
-#define GWTF_DISPATCH_FP(F, CALL)                     \
-    switch (padded_features(F)) {                     \
-        case 8:  { constexpr int FP = 8;  CALL; } break;  \
-        case 16: { constexpr int FP = 16; CALL; } break;  \
-        case 24: { constexpr int FP = 24; CALL; } break;  \
-        case 32: { constexpr int FP = 32; CALL; } break;  \
-        case 36: { constexpr int FP = 36; CALL; } break;  \
-        case 40: { constexpr int FP = 40; CALL; } break;  \
-        case 48: { constexpr int FP = 48; CALL; } break;  \
-        case 64: { constexpr int FP = 64; CALL; } break;  \
-        default: return fail(-4, "unsupported feature width"); \
-    }
-
-// ------------------------------------------------------------------------------------------
-template <int FP>
-int launch_eval(const EvalArgs& a0, cudaStream_t st) {
-    constexpr int P = PointsPerThread<FP>::fwd;
-    EvalArgs a = a0;
-    a.tiles_per_shape = (a.N + kThreads * P - 1) / (kThreads * P);
-    const int F = a.d.n_features;
-    const size_t smem = round_up((int)sizeof(EvalSmem<FP>), 16) + 2 * (size_t)round_up(raw_floats(F), 4) * 4;
-    GWTF_CUDA(allow_smem(k_nll_eval<FP, P>, smem));
-    k_nll_eval<FP, P><<<a.B * a.tiles_per_shape, kThreads, smem, st>>>(a);
-    GWTF_CUDA(cudaGetLastError());
-    return 0;
-}
-
-#define GWTF_DISPATCH_TC(F, CALL)                                         \
-    switch ((F + 8) / 8) {                                                \
-        case 1: { constexpr int FPK = 8,  FPN = 16; CALL; } break;        \
-        case 2: { constexpr int FPK = 16, FPN = 16; CALL; } break;        \
-        case 3: { constexpr int FPK = 24, FPN = 32; CALL; } break;        \
-        case 4: { constexpr int FPK = 32, FPN = 32; CALL; } break;        \
-        case 5: { constexpr int FPK = 40, FPN = 48; CALL; } break;        \
-        default: return fail(-4, "unsupported feature width for the tensor-core path"); \
-    }
-
-template <typename KernelT>
-int blocks_per_sm_n(KernelT kernel, int threads, size_t smem) {
-    int n = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, threads, smem);
-    return n < 1 ? 1 : n;
-}
-
-template <int FPK, int FPN, int PHASE>
-int launch_fwd_layer_tc(const LayerArgs& a0, cudaStream_t st) {
-    LayerArgs a = a0;
-    a.tiles_per_shape = (a.N + kTcThreads - 1) / kTcThreads;
-    const int F = a.d.n_features;
-    const size_t smem = round_up((int)sizeof(TcFwdSmem<FPK, FPN>), 16) + (size_t)round_up(raw_floats(F), 4) * 4;
-    auto kern = k_fwd_layer_tc<FPK, FPN, PHASE>;
-    GWTF_CUDA(allow_smem(kern, smem));
-    const int tiles = a.B * a.tiles_per_shape;
-    const int K = a.d.n_components;
-    // the occupancy API reports 1 CTA/SM for tcgen05 kernels; size the grid from the real limits
-    // (shared memory, tensor-memory columns) -- the hardware co-schedules what fits
-    int per_sm = (int)((227 * 1024) / (smem + 1024));
-    (void)blocks_per_sm_n(kern, kTcThreads, smem);
-    if (getenv("GWTF_DEBUG")) {
-        static int once = 0;
-        if (!once++) fprintf(stderr, "[gwtf] tc fwd: occupancy %d CTAs/SM, smem %zu, sms %d, err=%s\n", per_sm, smem, num_sms(), cudaGetErrorString(cudaPeekAtLastError()));
-    }
-    if (per_sm > 512 / kTcCols) per_sm = 512 / kTcCols;          // tensor-memory columns per SM
-    int gx = (num_sms() * per_sm + K - 1) / K;
-    if (gx > tiles) gx = tiles;
-    if (gx < 1) gx = 1;
-    kern<<<dim3(gx, K), kTcThreads, smem, st>>>(a);
-    GWTF_CUDA(cudaGetLastError());
-    return 0;
-}
-
-template <int FPK, int FPN, int PHASE>
-int launch_fwd_layer_tcp(const LayerArgs& a0, cudaStream_t st) {
-    LayerArgs a = a0;
-    a.tiles_per_shape = (a.N + 127) / 128;
-    const int F = a.d.n_features, K = a.d.n_components;
-    const size_t smem = round_up((int)sizeof(TcPersistSmem<FPK, FPN>), 16) + (size_t)round_up(raw_floats(F), 4) * 4;
-    auto kern = k_fwd_layer_tcp<FPK, FPN, PHASE>;
-    GWTF_CUDA(allow_smem(kern, smem));
-    const int tiles = a.B * a.tiles_per_shape;
-    int gx = num_sms() / K;                                  // one CTA per SM owns all 512 TMEM columns
-    if (gx > (tiles + kSlots - 1) / kSlots) gx = (tiles + kSlots - 1) / kSlots;
-    if (gx < 1) gx = 1;
-    GWTF_CUDA(launch_pdl(kern, dim3(gx, K), dim3(kPersistThreads), smem, st, a));
-    return 0;
-}
-
-template <int FP, int PHASE>
-int launch_fwd_layer_mma(const LayerArgs& a, cudaStream_t st) {
-    // statistics pass: 2 m-tiles per warp (shared B fragments, 2 MMA chains), full register file, 1 CTA/SM;
-    // apply pass: 1 m-tile per warp, 128 registers, 2 CTAs/SM
-    constexpr int MI = PHASE == 0 ? 2 : 1;
-    const int F = a.d.n_features, K = a.d.n_components;
-    const size_t smem = fwd_mma_smem<FP>(F);
-    auto kern = k_fwd_layer_mma<FP, PHASE, MI>;
-    GWTF_CUDA(allow_smem(kern, smem));
-    const long long tiles = (long long)a.B * ((a.N + 128 * MI - 1) / (128 * MI));
-    int gx = (MI == 1 ? 2 : 1) * num_sms() / K;              // contiguous tile ranges
-    if (gx > tiles) gx = (int)tiles;
-    kern<<<dim3(gx < 1 ? 1 : gx, K), kThreads, smem, st>>>(a, PHASE == 1 ? a.y1out : nullptr);
-    GWTF_CUDA(cudaGetLastError());
-    return 0;
-}
-
-#define GWTF_DISPATCH_FP8(F, CALL)                        \
-    switch (((F) + 7) / 8 * 8) {                          \
-        case 8:  { constexpr int FP = 8;  CALL; } break;  \
-        case 16: { constexpr int FP = 16; CALL; } break;  \
-        case 24: { constexpr int FP = 24; CALL; } break;  \
-        case 32: { constexpr int FP = 32; CALL; } break;  \
-        case 40: { constexpr int FP = 40; CALL; } break;  \
-        case 48: { constexpr int FP = 48; CALL; } break;  \
-        case 56: { constexpr int FP = 56; CALL; } break;  \
-        case 64: { constexpr int FP = 64; CALL; } break;  \
-        default: return fail(-4, "unsupported feature width"); \
-    }
-
-// floats per layer of the kept-activation buffer under the current engine
-size_t keep_layer_floats(int F, int K, int B, int N) {
-    return fwd_engine(F) != 0 ? (size_t)K * mma_keep_floats(F, B, N) : (size_t)K * 2 * F * B * N;
-}
-
-template <int FP, int PHASE>
-int launch_fwd_layer(const LayerArgs& a0, cudaStream_t st) {
-    constexpr int P = PointsPerThread<FP>::fwd;
-    LayerArgs a = a0;
-    a.tiles_per_shape = (a.N + kThreads * P - 1) / (kThreads * P);
-    const int F = a.d.n_features;
-    const size_t smem = round_up((int)sizeof(PhaseSmem<FP>), 16) + (size_t)round_up(raw_floats(F), 4) * 4;
-    auto kern = k_fwd_layer<FP, P, PHASE>;
-    GWTF_CUDA(allow_smem(kern, smem));
-    const int tiles = a.B * a.tiles_per_shape;
-    const int K = a.d.n_components;
-    int gx = (num_sms() * blocks_per_sm(kern, smem) + K - 1) / K;
-    if (gx > tiles) gx = tiles;
-    if (gx < 1) gx = 1;
-    kern<<<dim3(gx, K), kThreads, smem, st>>>(a);
-    GWTF_CUDA(cudaGetLastError());
-    return 0;
 }
 
 }  // namespace
 
+namespace {
+__global__ void __launch_bounds__(256) k_adam(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                              float* __restrict__ v, float* __restrict__ vmax, long long n, float lr,
+                                              float beta1, float beta2, float eps, float wd, float bc1, float bc2) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const float gi = g[i];
+        const float mi = m[i] * beta1 + (1.0f - beta1) * gi;
+        float vi = v[i] * beta2;
+        vi = vi + (1.0f - beta2) * gi * gi;
+        m[i] = mi;
+        v[i] = vi;
+        float den = vi;
+        if (vmax) { den = fmaxf(vmax[i], vi); vmax[i] = den; }
+        const float denom = sqrtf(den) / bc2 + eps;
+        const float mc = mi / bc1;
+        const float pi = p[i];
+        p[i] = wd != 0.0f ? pi - (pi * wd + lr * (mc / denom)) : pi - lr * (mc / denom);
+    }
+}
+}  // namespace
+
+namespace {
+// issue-rate probe of the warp-level tensor-core path: 16 independent m16n8k8 tf32 accumulators per warp
+__global__ void __launch_bounds__(256) k_mma_probe(float* out, int iters) {
+    float d[16][4];
+    uint32_t a[4], bq[2];
+    for (int i = 0; i < 4; ++i) a[i] = __float_as_uint(1.0f + threadIdx.x * 1e-3f + i);
+    for (int i = 0; i < 2; ++i) bq[i] = __float_as_uint(0.5f + i);
+#pragma unroll
+    for (int n = 0; n < 16; ++n) d[n][0] = d[n][1] = d[n][2] = d[n][3] = 0.f;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int n = 0; n < 16; ++n) mma_tf32(d[n], a, bq[0], bq[1]);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int n = 0; n < 16; ++n) s += d[n][0] + d[n][1] + d[n][2] + d[n][3];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+__global__ void __launch_bounds__(256) k_ffma_probe(float* out, int iters, float a, float b) {
+    float acc[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) acc[i] = threadIdx.x * 1e-3f + i;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) acc[i] = fmaf(acc[i], a, b);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) s += acc[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+template <typename Launch>
+int time_probe(Launch launch, int grid, float& best_ms, cudaStream_t st) {
+    float* out = nullptr;
+    GWTF_CUDA(cudaMalloc(&out, sizeof(float) * grid * 256));
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    launch(out);
+    best_ms = 1e30f;
+    for (int r = 0; r < 5; ++r) {
+        cudaEventRecord(e0, st);
+        launch(out);
+        cudaEventRecord(e1, st);
+        cudaEventSynchronize(e1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (ms < best_ms) best_ms = ms;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaError_t err = cudaGetLastError();
+    cudaFree(out);
+    if (err != cudaSuccess) return cuda_fail(err, "roofline probe");
+    return 0;
+}
+}  // namespace
+
 extern "C" {
 
-int gwtf_version(void) { return 1; }
+int gwtf_version(void) { return 2; }
+const char* gwtf_last_error_string(void) { return err_buf(); }
 
-int gwtf_set_tensor_cores(int32_t enable) {
-    const int prev = g_use_tc;
-    g_use_tc = enable < 0 ? -1 : (enable > 3 ? 3 : enable);
-    return prev;
+int gwtf_resolved_engine(const gwtf_stack_desc* desc, int32_t which) {
+    if (check_desc(desc)) return -1;
+    return which == 0 ? fwd_engine(*desc) : bwd_engine(*desc);
 }
-const char* gwtf_last_error_string(void) { return g_err; }
-
-int gwtf_set_pdl(int32_t enable) {
-    const int prev = g_pdl;
-    g_pdl = enable < 0 ? -1 : (enable ? 1 : 0);
-    return prev;
-}
-int gwtf_engine(void) { tc_mode(1); return g_use_tc; }
 
 int64_t gwtf_keep_floats(const gwtf_stack_desc* desc, int32_t B, int32_t N) {
     if (check_desc(desc) || B <= 0 || N <= 0) return 0;
-    return (int64_t)desc->n_layers * (int64_t)keep_layer_floats(desc->n_features, desc->n_components, B, N);
+    return (int64_t)desc->n_layers * (int64_t)keep_layer_floats(*desc, B, N);
 }
 
 int gwtf_rec_stride(int32_t F) { return rec_stride_of(F); }
@@ -324,20 +194,14 @@ int gwtf_nll_fwd_eval(const gwtf_stack_desc* desc, const float* params, const fl
     EvalArgs a;
     a.d = *desc; a.params = params; a.bnbuf = bnbuf; a.film = film; a.points = points; a.base = base; a.logw = logw;
     a.B = B; a.N = N; a.nll = nll; a.logp = logp; a.z = z; a.ssum = ssum; a.tiles_per_shape = 0;
-    GWTF_DISPATCH_FP(desc->n_features, return launch_eval<FP>(a, (cudaStream_t)stream));
-    return 0;
+    return launch_eval_fma(a, (cudaStream_t)stream);
 }
 
 int gwtf_fwd_moments(const gwtf_stack_desc* desc, const float* points, int32_t B, int32_t N, double* mom, void* stream) {
     if (int rc = check_desc(desc)) return rc;
     if (!points || !mom) return fail(-10, "null pointer argument");
     if (B <= 0 || N <= 0) return 0;
-    size_t total = (size_t)B * N;
-    int grid = (int)((total + kThreads * 8 - 1) / (kThreads * 8));
-    if (grid > 4 * num_sms()) grid = 4 * num_sms();
-    k_moments<<<grid, kThreads, 0, (cudaStream_t)stream>>>(points, B, N, desc->n_components, mom);
-    GWTF_CUDA(cudaGetLastError());
-    return 0;
+    return launch_moments(points, B, N, desc->n_components, mom, (cudaStream_t)stream);
 }
 
 // NOTE: the C ABI takes explicit per-layer pointers so a multi-rank caller can all-reduce
@@ -359,24 +223,8 @@ int gwtf_fwd_layer_ex(const gwtf_stack_desc* desc, int32_t layer, int32_t phase,
     a.d = *desc; a.layer = layer; a.train = train; a.direct = direct; a.params = params; a.bnbuf = bnbuf; a.film = film;
     a.xin = xin; a.xin_shared = xin_shared; a.xout = xout; a.ld = ld; a.ssum = ssum; a.trio = trio; a.y1out = y1out;
     a.mom_in = mom_in; a.mom_out = mom_out; a.sum1 = sum1; a.B = B; a.N = N; a.n_total = n_total; a.tiles_per_shape = 0;
-    if (use_mma_fwd(desc->n_features)) {
-        if (phase == 0) { GWTF_DISPATCH_FP8(desc->n_features, return (launch_fwd_layer_mma<FP, 0>(a, (cudaStream_t)stream))); }
-        else { GWTF_DISPATCH_FP8(desc->n_features, return (launch_fwd_layer_mma<FP, 1>(a, (cudaStream_t)stream))); }
-        return 0;
-    }
-    if (fwd_engine(desc->n_features) == 2 && desc->n_components <= num_sms()) {
-        if (phase == 0) { GWTF_DISPATCH_TC(desc->n_features, return (launch_fwd_layer_tcp<FPK, FPN, 0>(a, (cudaStream_t)stream))); }
-        else { GWTF_DISPATCH_TC(desc->n_features, return (launch_fwd_layer_tcp<FPK, FPN, 1>(a, (cudaStream_t)stream))); }
-        return 0;
-    }
-    if (use_tc(desc->n_features)) {
-        if (phase == 0) { GWTF_DISPATCH_TC(desc->n_features, return (launch_fwd_layer_tc<FPK, FPN, 0>(a, (cudaStream_t)stream))); }
-        else { GWTF_DISPATCH_TC(desc->n_features, return (launch_fwd_layer_tc<FPK, FPN, 1>(a, (cudaStream_t)stream))); }
-        return 0;
-    }
-    if (phase == 0) { GWTF_DISPATCH_FP(desc->n_features, return (launch_fwd_layer<FP, 0>(a, (cudaStream_t)stream))); }
-    else { GWTF_DISPATCH_FP(desc->n_features, return (launch_fwd_layer<FP, 1>(a, (cudaStream_t)stream))); }
-    return 0;
+    a.seg = nullptr; a.seg_tiles = nullptr;
+    return fwd_layer_dispatch(a, phase, (cudaStream_t)stream);
 }
 
 int gwtf_fwd_layer(const gwtf_stack_desc* desc, int32_t layer, int32_t phase, int32_t train, const float* params,
@@ -392,7 +240,7 @@ int gwtf_fwd_layer(const gwtf_stack_desc* desc, int32_t layer, int32_t phase, in
     double* mom_in = mom ? mom + (size_t)layer * K * GWTF_MOM_STRIDE : nullptr;
     double* mom_out = (mom && layer > 0) ? mom + (size_t)(layer - 1) * K * GWTF_MOM_STRIDE : nullptr;
     double* s1 = sum1 ? sum1 + (size_t)layer * K * 4 * F : nullptr;
-    float* y1 = ybuf ? ybuf + (size_t)layer * keep_layer_floats(F, K, B, N) : nullptr;
+    float* y1 = ybuf ? ybuf + (size_t)layer * keep_layer_floats(*desc, B, N) : nullptr;
     return gwtf_fwd_layer_ex(desc, layer, phase, train, 0, params, bnbuf, film, xin, first ? 1 : 0,
                              ubuf + (size_t)layer * slot, ld, ssum, nullptr, y1, mom_in, train ? mom_out : nullptr, s1,
                              B, N, n_total, stream);
@@ -402,10 +250,7 @@ int gwtf_fwd_bstat(const gwtf_stack_desc* desc, const float* params, const doubl
                    double n_total, float* bstat, void* stream) {
     if (int rc = check_desc(desc)) return rc;
     if (!params || !mom || !sum1 || !bstat) return fail(-10, "null pointer argument");
-    const int total = desc->n_layers * desc->n_components * 2 * desc->n_features;
-    k_bstat<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(*desc, params, mom, sum1, n_total, bstat);
-    GWTF_CUDA(cudaGetLastError());
-    return 0;
+    return launch_bstat(*desc, params, mom, sum1, n_total, bstat, (cudaStream_t)stream);
 }
 
 int gwtf_nll_from_state(const gwtf_stack_desc* desc, const float* ubuf, const float* ld, const float* base,
@@ -413,26 +258,31 @@ int gwtf_nll_from_state(const gwtf_stack_desc* desc, const float* ubuf, const fl
     if (int rc = check_desc(desc)) return rc;
     if (!ubuf || !ld || !base || !logw || !nll) return fail(-10, "null pointer argument");
     if (B <= 0 || N <= 0) return 0;
-    const size_t total = (size_t)B * N;
-    k_nll_from_state<<<(unsigned)((total + kThreads - 1) / kThreads), kThreads, 0, (cudaStream_t)stream>>>(
-        desc->n_components, B, N, ubuf, ld, base, logw, nll, logp);
-    GWTF_CUDA(cudaGetLastError());
-    return 0;
+    return launch_nll_from_state(*desc, B, N, ubuf, ld, base, logw, nll, logp, (cudaStream_t)stream);
 }
 
-// Eval-mode NLL through the per-layer kernels of the current engine (tensor cores): L launches that ping-pong
-// between two (K,B,3,N) slots of `scratch`, then the mixture head.  Faster than the single-launch FMA kernel
-// at every size measured on B200 (64 x 2048: 2.2 vs 3.3 ms; 4 x 2048: 0.5 vs 3.3 ms).
+int64_t gwtf_eval_layers_workspace_bytes(const gwtf_stack_desc* desc, int32_t B, int32_t N) {
+    if (check_desc(desc) || B <= 0 || N <= 0) return 0;
+    const int64_t K = desc->n_components;
+    return 4 * (2 * K * B * 3 * N + K * B * N);              // two ping-pong coordinate slots + the log-det sums
+}
+
+// Eval-mode NLL through the per-layer kernels of the descriptor's engine (tensor cores): L launches that
+// ping-pong between two (K,B,3,N) slots of the workspace, then the mixture head.  Faster than the single-launch
+// FMA kernel at every size measured on B200.  Honours desc->eval_precision.
 int gwtf_nll_fwd_eval_layers(const gwtf_stack_desc* desc, const float* params, const float* bnbuf, const float* film,
-                             const float* points, const float* base, const float* logw, float* scratch, float* ld,
-                             int32_t B, int32_t N, float* nll, float* logp, void* stream) {
+                             const float* points, const float* base, const float* logw, void* workspace,
+                             int64_t workspace_bytes, int32_t B, int32_t N, float* nll, float* logp, void* stream) {
     if (int rc = check_desc(desc)) return rc;
-    if (!params || !bnbuf || !film || !points || !base || !logw || !scratch || !ld || !nll)
+    if (!params || !bnbuf || !film || !points || !base || !logw || !workspace || !nll)
         return fail(-10, "null pointer argument");
     if (B <= 0 || N <= 0) return 0;
+    if (workspace_bytes < gwtf_eval_layers_workspace_bytes(desc, B, N)) return fail(-25, "workspace too small");
     cudaStream_t st = (cudaStream_t)stream;
     const int L = desc->n_layers, K = desc->n_components;
     const size_t slot = (size_t)K * B * 3 * N;
+    float* scratch = (float*)workspace;
+    float* ld = scratch + 2 * slot;
     GWTF_CUDA(cudaMemsetAsync(ld, 0, sizeof(float) * (size_t)K * B * N, st));
     const float* xin = points;
     for (int l = L - 1; l >= 0; --l) {
@@ -445,26 +295,41 @@ int gwtf_nll_fwd_eval_layers(const gwtf_stack_desc* desc, const float* params, c
     return gwtf_nll_from_state(desc, scratch, ld, base, logw, B, N, nll, logp, stream);
 }
 
-int gwtf_exchange_attach(int32_t rank, int32_t world, void* const* recv, void* const* flags, int32_t slot_doubles) {
+int gwtf_exchange_create(int32_t rank, int32_t world, void* const* recv, void* const* flags, int32_t slot_doubles,
+                         double timeout_s, gwtf_exchange** out) {
+    if (!out) return fail(-10, "null pointer argument");
+    *out = nullptr;
     if (world < 1 || world > kMaxRanks || rank < 0 || rank >= world) return fail(-21, "bad rank / world size");
     if (world > 1 && (!recv || !flags || slot_doubles <= 0)) return fail(-21, "exchange buffers missing");
-    g_xchg = ExchangeCtx();
-    g_xchg.rank = rank; g_xchg.world = world; g_xchg.slot = slot_doubles;
-    for (int r = 0; r < world && world > 1; ++r) {
+    for (int r = 0; r < world && world > 1; ++r)
         if (!recv[r] || !flags[r]) return fail(-21, "null peer pointer");
-        g_xchg.recv[r] = (double*)recv[r];
-        g_xchg.flags[r] = (unsigned long long*)flags[r];
+    gwtf_exchange* x = new (std::nothrow) gwtf_exchange();
+    if (!x) return fail(-26, "out of host memory");
+    x->rank = rank; x->world = world; x->slot = slot_doubles;
+    if (timeout_s > 0.0) x->timeout_ns = (unsigned long long)(timeout_s * 1e9);
+    for (int r = 0; r < world && world > 1; ++r) {
+        x->recv[r] = (double*)recv[r];
+        x->flags[r] = (unsigned long long*)flags[r];
     }
+    *out = x;
     return 0;
 }
-int gwtf_exchange_world(void) { return g_xchg.world; }
-int gwtf_exchange_sum(double* data, int32_t n, void* stream) {
+int gwtf_exchange_destroy(gwtf_exchange* x) { delete x; return 0; }
+int gwtf_exchange_world(const gwtf_exchange* x) { return x ? x->world : 1; }
+uint64_t gwtf_exchange_seq(const gwtf_exchange* x) { return x ? x->seq : 0; }
+int gwtf_exchange_resync(gwtf_exchange* x, uint64_t seq) {
+    if (!x) return fail(-10, "null pointer argument");
+    if (seq < x->seq) return fail(-27, "the sequence number may only move forward (peers wait for >= seq)");
+    x->seq = seq;
+    return 0;
+}
+int gwtf_exchange_sum(gwtf_exchange* x, double* data, int32_t n, void* stream) {
     if (!data || n <= 0) return fail(-10, "null pointer argument");
-    return exchange_sum(data, n, (cudaStream_t)stream);
+    return exchange_sum(x, data, n, true, (cudaStream_t)stream);
 }
 
 // n_total > 0: statistics are over n_total points on all ranks; the sums are exchanged between phases
-// through the attached peer-memory exchange
+// through desc->exchange
 static int fwd_all_impl(const gwtf_stack_desc* desc, int32_t train, const float* params, const float* bnbuf,
                         const float* film, const float* points, const float* base, const float* logw, float* ubuf,
                         float* ld, float* ssum, float* ybuf, double* mom, double* sum1, float* bstat, int32_t B,
@@ -475,7 +340,9 @@ static int fwd_all_impl(const gwtf_stack_desc* desc, int32_t train, const float*
     cudaStream_t st = (cudaStream_t)stream;
     const int L = desc->n_layers, K = desc->n_components, F = desc->n_features;
     const bool ranks = n_total_in > 0.0 && train;
-    if (ranks && g_xchg.world <= 1) return fail(-22, "gwtf_exchange_attach has not been called");
+    gwtf_exchange* x = desc->exchange;
+    if (ranks && (!x || x->world <= 1)) return fail(-22, "the descriptor carries no rank exchange (gwtf_exchange_create)");
+    const bool pdl = pdl_on(*desc);
     const double n_total = n_total_in > 0.0 ? n_total_in : (double)B * (double)N;
     GWTF_CUDA(cudaMemsetAsync(ld, 0, sizeof(float) * (size_t)K * B * N, st));
     if (ssum) GWTF_CUDA(cudaMemsetAsync(ssum, 0, sizeof(float) * (size_t)K * B * 3 * N, st));
@@ -487,10 +354,10 @@ static int fwd_all_impl(const gwtf_stack_desc* desc, int32_t train, const float*
     }
     for (int l = L - 1; l >= 0; --l) {
         if (train) {
-            if (ranks) if (int rc = exchange_sum(mom + (size_t)l * K * GWTF_MOM_STRIDE, K * GWTF_MOM_STRIDE, st)) return rc;
+            if (ranks) if (int rc = exchange_sum(x, mom + (size_t)l * K * GWTF_MOM_STRIDE, K * GWTF_MOM_STRIDE, pdl, st)) return rc;
             if (int rc = gwtf_fwd_layer(desc, l, 0, 1, params, bnbuf, film, points, ubuf, ld, ssum, ybuf, mom, sum1, B,
                                         N, n_total, stream)) return rc;
-            if (ranks) if (int rc = exchange_sum(sum1 + (size_t)l * K * 4 * F, K * 4 * F, st)) return rc;
+            if (ranks) if (int rc = exchange_sum(x, sum1 + (size_t)l * K * 4 * F, K * 4 * F, pdl, st)) return rc;
         }
         if (int rc = gwtf_fwd_layer(desc, l, 1, train, params, bnbuf, film, points, ubuf, ld, ssum, ybuf, mom, sum1, B,
                                     N, n_total, stream)) return rc;
@@ -517,6 +384,238 @@ int gwtf_fwd_all_ranks(const gwtf_stack_desc* desc, int32_t train, const float* 
                         nll, logp, n_total, stream);
 }
 
-#include "gwtf_api_bwd.inc"
+// ------------------------------------------------------------------------------------------ backward
+int gwtf_bwd_seed(const gwtf_stack_desc* desc, const float* ubuf, const float* ld, const float* base,
+                  const float* logw, const float* nll, const float* dnll, int32_t B, int32_t N, float* gbuf, float* gs,
+                  float* dbase, float* dlogw, void* stream) {
+    if (int rc = check_desc(desc)) return rc;
+    if (!ubuf || !ld || !base || !logw || !nll || !dnll || !gbuf || !gs || !dbase || !dlogw)
+        return fail(-10, "null pointer argument");
+    if (B <= 0 || N <= 0) return 0;
+    return launch_bwd_seed(desc->n_components, B, N, ubuf, ld, base, logw, nll, dnll, gbuf, gs, dbase, dlogw,
+                           (cudaStream_t)stream);
+}
+
+int gwtf_bwd_layer(const gwtf_stack_desc* desc, int32_t layer, int32_t phase, int32_t train, const float* params,
+                   const float* bnbuf, const float* film, const float* points, const float* ubuf, const float* ybuf,
+                   const double* mom, const double* sum1, double* bsum, float* gbuf, const float* gs, float* dobuf,
+                   float* dparams, float* dfilm, int32_t B, int32_t N, double n_total, void* stream) {
+    if (int rc = check_desc(desc)) return rc;
+    const int L = desc->n_layers, K = desc->n_components, F = desc->n_features;
+    if (layer < 0 || layer >= L) return fail(-12, "layer out of range");
+    if (phase != 0 && phase != 1) return fail(-13, "phase must be 0 or 1");
+    if (!params || !film || !points || !ubuf || !bsum || !gbuf || !gs || !dobuf || !dparams || !dfilm)
+        return fail(-10, "null pointer argument");
+    if (train && (!mom || !sum1)) return fail(-10, "train mode needs mom and sum1");
+    if (!train && !bnbuf) return fail(-10, "eval mode needs bnbuf");
+    if (B <= 0 || N <= 0) return 0;
+    const size_t slot = (size_t)K * B * 3 * N;
+    const bool first = layer == L - 1;
+    BwdArgs a;
+    a.d = *desc; a.layer = layer; a.train = train; a.params = params; a.bnbuf = bnbuf; a.film = film;
+    a.xin = first ? points : ubuf + (size_t)(layer + 1) * slot;
+    a.xin_shared = first ? 1 : 0;
+    a.xout = ubuf + (size_t)layer * slot;
+    a.y1in = ybuf ? ybuf + (size_t)layer * keep_layer_floats(*desc, B, N) : nullptr;
+    a.kept_y1 = (a.y1in && fwd_engine(*desc) == kEngineTcFwd) ? 1 : 0;
+    a.mom_in = mom ? mom + (size_t)layer * K * GWTF_MOM_STRIDE : nullptr;
+    a.sum1 = sum1 ? sum1 + (size_t)layer * K * 4 * F : nullptr;
+    a.bsum = bsum + (size_t)layer * K * 8 * F;
+    a.mom_prev = (train && layer > 0) ? mom + (size_t)(layer - 1) * K * GWTF_MOM_STRIDE : nullptr;
+    a.bsum_prev = (train && layer > 0) ? bsum + (size_t)(layer - 1) * K * 8 * F : nullptr;
+    a.gbuf = gbuf; a.gs = gs; a.dobuf = dobuf; a.dparams = dparams; a.dfilm = dfilm;
+    a.B = B; a.N = N; a.n_total = n_total; a.tiles_per_shape = 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (bwd_engine(*desc)) {
+        case kEngineFma: return launch_bwd_layer_fma(a, phase, st);
+        case kEngineTc: a.y1in = nullptr; a.kept_y1 = 0; return launch_bwd_layer_tc(a, phase, st);
+        default: return launch_bwd_layer_mma(a, phase, st);
+    }
+}
+
+int gwtf_bwd_finish(const gwtf_stack_desc* desc, int32_t train, const float* params, const float* bnbuf,
+                    const double* mom, const double* bsum, const float* gbuf, const float* points, float* dparams,
+                    float* dpoints, int32_t B, int32_t N, double n_total, void* stream) {
+    if (int rc = check_desc(desc)) return rc;
+    if (!params || !dparams) return fail(-10, "null pointer argument");
+    if (train && (!mom || !bsum)) return fail(-10, "train mode needs mom and bsum");
+    if (!train && !bnbuf) return fail(-10, "eval mode needs bnbuf");
+    if (B <= 0 || N <= 0) return 0;
+    if (dpoints && (!gbuf || !points)) return fail(-10, "dpoints needs gbuf and points");
+    FinishArgs fa;
+    fa.d = *desc; fa.train = train; fa.params = params; fa.bnbuf = bnbuf; fa.mom = mom; fa.bsum = bsum;
+    fa.dparams = dparams; fa.n_total = n_total; fa.local_frac = ((double)B * (double)N) / n_total;
+    return launch_bwd_finish(fa, *desc, train, params, mom, bsum, gbuf, points, dpoints, B, N, n_total,
+                             (cudaStream_t)stream);
+}
+
+static int bwd_all_impl(const gwtf_stack_desc* desc, int32_t train, const float* params, const float* bnbuf,
+                        const float* film, const float* points, const float* base, const float* logw, const float* ubuf,
+                        const float* ybuf, const float* ld, const double* mom, const double* sum1, const float* nll,
+                        const float* dnll, double* bsum, float* gbuf, float* gs, float* dobuf, float* dparams,
+                        float* dfilm, float* dbase, float* dlogw, float* dpoints, int32_t B, int32_t N,
+                        double n_total_in, void* stream) {
+    if (int rc = check_desc(desc)) return rc;
+    if (B <= 0 || N <= 0) return 0;
+    const bool ranks = n_total_in > 0.0 && train;
+    gwtf_exchange* x = desc->exchange;
+    if (ranks && (!x || x->world <= 1)) return fail(-22, "the descriptor carries no rank exchange (gwtf_exchange_create)");
+    const double n_total = n_total_in > 0.0 ? n_total_in : (double)B * (double)N;
+    const int K = desc->n_components, F = desc->n_features;
+    if (dnll) {   // seeds from the in-kernel NLL; otherwise gbuf / gs already hold dL/dz, dL/dS
+        if (int rc = gwtf_bwd_seed(desc, ubuf, ld, base, logw, nll, dnll, B, N, gbuf, gs, dbase, dlogw, stream)) return rc;
+    }
+    for (int l = 0; l < desc->n_layers; ++l)
+        for (int phase = 0; phase < 2; ++phase) {
+            if (int rc = gwtf_bwd_layer(desc, l, phase, train, params, bnbuf, film, points, ubuf, ybuf, mom, sum1, bsum,
+                                        gbuf, gs, dobuf, dparams, dfilm, B, N, n_total, stream)) return rc;
+            // phase 0 completes the sd1_bn sums (slots 0,1), phase 1 the bn0 sums (slots 2,3); the slots of
+            // the other phase ride along (nobody reads slots 0,1 after phase 1)
+            if (ranks) if (int rc = exchange_sum(x, bsum + (size_t)l * K * 8 * F, K * 8 * F, pdl_on(*desc), (cudaStream_t)stream)) return rc;
+        }
+    return gwtf_bwd_finish(desc, train, params, bnbuf, mom, bsum, gbuf, points, dparams, dpoints, B, N, n_total, stream);
+}
+
+int gwtf_bwd_all(const gwtf_stack_desc* desc, int32_t train, const float* params, const float* bnbuf,
+                 const float* film, const float* points, const float* base, const float* logw, const float* ubuf,
+                 const float* ybuf, const float* ld, const double* mom, const double* sum1, const float* nll,
+                 const float* dnll,
+                 double* bsum, float* gbuf, float* gs, float* dobuf, float* dparams, float* dfilm, float* dbase,
+                 float* dlogw, float* dpoints, int32_t B, int32_t N, void* stream) {
+    return bwd_all_impl(desc, train, params, bnbuf, film, points, base, logw, ubuf, ybuf, ld, mom, sum1, nll, dnll, bsum,
+                        gbuf, gs, dobuf, dparams, dfilm, dbase, dlogw, dpoints, B, N, 0.0, stream);
+}
+int gwtf_bwd_all_ranks(const gwtf_stack_desc* desc, int32_t train, const float* params, const float* bnbuf,
+                       const float* film, const float* points, const float* base, const float* logw, const float* ubuf,
+                       const float* ybuf, const float* ld, const double* mom, const double* sum1, const float* nll,
+                       const float* dnll, double* bsum, float* gbuf, float* gs, float* dobuf, float* dparams,
+                       float* dfilm, float* dbase, float* dlogw, float* dpoints, int32_t B, int32_t N, double n_total,
+                       void* stream) {
+    if (!(n_total > 0.0)) return fail(-23, "n_total must be the number of points on all ranks");
+    return bwd_all_impl(desc, train, params, bnbuf, film, points, base, logw, ubuf, ybuf, ld, mom, sum1, nll, dnll, bsum,
+                        gbuf, gs, dobuf, dparams, dfilm, dbase, dlogw, dpoints, B, N, n_total, stream);
+}
+
+// ------------------------------------------------------------------------------------------ sampling
+int gwtf_mixture_cdf(const float* logits, int32_t B, int32_t K, float* cdf, void* stream) {
+    if (!logits || !cdf) return fail(-10, "null pointer argument");
+    if (K < 1 || K > GWTF_MAX_COMPONENTS) return fail(-2, "n_components out of range");
+    if (B <= 0) return 0;
+    return launch_mixture_cdf(logits, B, K, cdf, (cudaStream_t)stream);
+}
+
+int gwtf_sample(const gwtf_stack_desc* desc, const float* params, const float* bnbuf, const float* film,
+                const float* base, const float* cdf, int32_t B, int32_t N, uint64_t seed, uint32_t stream_id,
+                const int32_t* idx_in, const float* eps_in, float* samples, int32_t* labels, float* z_out, void* stream) {
+    if (int rc = check_desc(desc)) return rc;
+    if (!params || !bnbuf || !film || !base || !cdf || !samples || !labels) return fail(-10, "null pointer argument");
+    if (B <= 0 || N <= 0) return 0;
+    SampleArgs a;
+    a.d = *desc; a.params = params; a.bnbuf = bnbuf; a.film = film; a.base = base; a.cdf = cdf; a.B = B; a.N = N;
+    a.seed_lo = (uint32_t)(seed & 0xFFFFFFFFull);
+    a.stream_id = stream_id ^ (uint32_t)(seed >> 32);
+    a.idx_in = idx_in; a.eps_in = eps_in; a.samples = samples; a.labels = labels; a.z_out = z_out;
+    a.tiles_per_shape = 0; a.tile_points = 0;
+    return launch_sample_fma(a, (cudaStream_t)stream);
+}
+
+static int64_t sample_npad(int K, int N) { return (int64_t)(N + 127) / 128 * 128 + 128 * (int64_t)K; }
+
+int64_t gwtf_sample_workspace_bytes(const gwtf_stack_desc* desc, int32_t B, int32_t N) {
+    if (check_desc(desc) || B <= 0 || N <= 0) return 0;
+    const int64_t K = desc->n_components, npad = sample_npad((int)K, N);
+    // two ping-pong coordinate rows | slot (B,N) | counts, cursor (B,K) | seg (K,B,2) | seg_tiles (K,B+1)
+    return 4 * (2 * B * 3 * npad + (int64_t)B * N + 2 * B * K + 2 * K * B + K * (B + 1)) + 64;
+}
+
+int gwtf_sample_layers(const gwtf_stack_desc* desc, const float* params, const float* bnbuf, const float* film,
+                       const float* base, const float* cdf, int32_t B, int32_t N, uint64_t seed, uint32_t stream_id,
+                       const int32_t* idx_in, const float* eps_in, void* workspace, int64_t workspace_bytes,
+                       float* samples, int32_t* labels, float* z_out, void* stream) {
+    if (int rc = check_desc(desc)) return rc;
+    if (!params || !bnbuf || !film || !base || !cdf || !workspace || !samples || !labels)
+        return fail(-10, "null pointer argument");
+    if (B <= 0 || N <= 0) return 0;
+    if (fwd_engine(*desc) != kEngineTcFwd) return fail(-4, "gwtf_sample_layers needs the tcgen05 forward (use gwtf_sample)");
+    if (workspace_bytes < gwtf_sample_workspace_bytes(desc, B, N)) return fail(-25, "workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int K = desc->n_components, L = desc->n_layers;
+    const int npad = (int)sample_npad(K, N);
+    const size_t row = (size_t)B * 3 * npad;
+    float* xbuf = (float*)workspace;
+    int32_t* slot = (int32_t*)(xbuf + 2 * row);
+    int32_t* counts = slot + (size_t)B * N;
+    int32_t* cursor = counts + (size_t)B * K;
+    int32_t* seg = cursor + (size_t)B * K;
+    int32_t* seg_tiles = seg + (size_t)2 * K * B;
+    GWTF_CUDA(cudaMemsetAsync(counts, 0, sizeof(int32_t) * (size_t)B * K, st));
+    const uint32_t seed_lo = (uint32_t)(seed & 0xFFFFFFFFull), sid = stream_id ^ (uint32_t)(seed >> 32);
+    SamplePlanArgs pa;
+    pa.K = K; pa.B = B; pa.N = N; pa.cdf = cdf; pa.idx_in = idx_in; pa.counts = counts; pa.seed_lo = seed_lo; pa.stream_id = sid;
+    if (int rc = launch_sample_count(pa, st)) return rc;
+    if (int rc = launch_sample_plan(K, B, counts, seg, seg_tiles, cursor, st)) return rc;
+    SampleScatterArgs sa;
+    sa.K = K; sa.B = B; sa.N = N; sa.Npad = npad; sa.base = base; sa.cdf = cdf; sa.idx_in = idx_in; sa.eps_in = eps_in;
+    sa.seed_lo = seed_lo; sa.stream_id = sid; sa.seg = seg; sa.cursor = cursor;
+    sa.xbuf = xbuf; sa.slot = slot; sa.labels = labels; sa.z_out = z_out;
+    if (int rc = launch_sample_scatter(sa, st)) return rc;
+    const float* xin = xbuf;
+    for (int l = 0; l < L; ++l) {               // direct order (flows.py:150-160)
+        float* xout = xbuf + (size_t)((l + 1) & 1) * row;
+        LayerArgs a;
+        a.d = *desc; a.layer = l; a.train = 0; a.direct = 1; a.params = params; a.bnbuf = bnbuf; a.film = film;
+        a.xin = xin; a.xin_shared = 1; a.xout = xout; a.ld = nullptr; a.ssum = nullptr; a.trio = nullptr; a.y1out = nullptr;
+        a.mom_in = nullptr; a.mom_out = nullptr; a.sum1 = nullptr; a.B = B; a.N = npad; a.n_total = 1.0;
+        a.tiles_per_shape = 0; a.seg = seg; a.seg_tiles = seg_tiles;
+        if (int rc = launch_fwd_layer_tc(a, 1, st)) return rc;
+        xin = xout;
+    }
+    return launch_sample_gather(B, N, npad, xin, slot, samples, st);
+}
+
+// ------------------------------------------------------------------------------------------ optimizer
+// Fused AMSGrad / Adam step over one flat buffer (lib/networks/optimizers.py:42-74): first / second moment EMAs,
+// running max of the second moment, bias corrections, and the reference's weight decay that is added to the
+// UPDATE un-scaled by lr (:69-72).  HBM-bound: 5 reads + 4 writes of 4 bytes per parameter.
+
+int gwtf_adam_step(float* p, const float* g, float* exp_avg, float* exp_avg_sq, float* max_exp_avg_sq, int64_t n,
+                   double lr, double beta1, double beta2, double eps, double weight_decay, int64_t step, void* stream) {
+    if (!p || !g || !exp_avg || !exp_avg_sq) return fail(-10, "null pointer argument");
+    if (n <= 0) return 0;
+    if (step < 1) return fail(-28, "step counts from 1");
+    const double bc1 = 1.0 - pow(beta1, (double)step), bc2 = sqrt(1.0 - pow(beta2, (double)step));
+    long long blocks = (n + 256 * 4 - 1) / (256 * 4);
+    const long long cap = 8LL * num_sms();
+    if (blocks > cap) blocks = cap;
+    k_adam<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(p, g, exp_avg, exp_avg_sq, max_exp_avg_sq, (long long)n,
+                                                               (float)lr, (float)beta1, (float)beta2, (float)eps,
+                                                               (float)weight_decay, (float)bc1, (float)bc2);
+    GWTF_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------ probes
+
+int gwtf_mma_peak_tflops(int32_t iters, double* tflops, void* stream) {
+    if (!tflops || iters <= 0) return fail(-1, "bad arguments to gwtf_mma_peak_tflops");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int grid = num_sms() * 2;
+    float best = 0.f;
+    if (int rc = time_probe([&](float* out) { k_mma_probe<<<grid, 256, 0, st>>>(out, iters); }, grid, best, st)) return rc;
+    // one m16n8k8 = 2*16*8*8 flops per warp instruction, 16 per iteration, 8 warps per CTA
+    *tflops = 2.0 * 16 * 8 * 8 * 16.0 * (double)iters * 8.0 * (double)grid / ((double)best * 1e-3) * 1e-12;
+    return 0;
+}
+
+int gwtf_fma_peak_tflops(int32_t iters, double* tflops, void* stream) {
+    if (!tflops || iters <= 0) return fail(-1, "bad arguments to gwtf_fma_peak_tflops");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int grid = num_sms() * 4;
+    float best = 0.f;
+    if (int rc = time_probe([&](float* out) { k_ffma_probe<<<grid, 256, 0, st>>>(out, iters, 1.0001f, 1e-4f); }, grid, best, st))
+        return rc;
+    *tflops = 2.0 * 32.0 * (double)iters * 256.0 * (double)grid / ((double)best * 1e-3) * 1e-12;
+    return 0;
+}
 
 }  // extern "C"

@@ -10,7 +10,7 @@ namespace gwtf {
 // Seeds: responsibilities r_j = softmax_j(logp_j + logw_j), dL/dz, dL/dS, base / weight grads.
 // grid (tiles, B): a CTA only sees points of one shape so per-shape sums reduce in-block.
 // =============================================================================================
-__global__ void __launch_bounds__(kThreads) k_bwd_seed(int K, int B, int N, const float* __restrict__ z,
+static __global__ void __launch_bounds__(kThreads) k_bwd_seed(int K, int B, int N, const float* __restrict__ z,
                                                        const float* __restrict__ ld, const float* __restrict__ base,
                                                        const float* __restrict__ logw, const float* __restrict__ nll,
                                                        const float* __restrict__ dnll, float* gbuf, float* gs,
@@ -632,7 +632,7 @@ struct FinishArgs {
 };
 
 // dW0[e][a] = i0*g0*( P_raw - (dbeta0/n) Sx_a - (dgamma0/n) i0 (W0[e] . Sxx[:,a] - m0 Sx_a) )
-__global__ void k_bwd_finish_w0(const FinishArgs a) {
+static __global__ void k_bwd_finish_w0(const FinishArgs a) {
     const int F = a.d.n_features, K = a.d.n_components, L = a.d.n_layers;
     const int total = L * K * 2 * F;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {

@@ -84,12 +84,12 @@ __global__ void __launch_bounds__(kThreads, 2) k_bwd_layer_e_mma(const BwdArgs a
     src.sum1 = a.sum1 ? a.sum1 + (size_t)j * 4 * F : nullptr;
     src.n_total = a.n_total;
 
-    pdl_trigger();
     if (tid == 0) { mbar_init(&S.bar, 1); mbar_fence_init(); }
     if (warp == 0) tmem_alloc(&S.tmem_base, BwdETmem<FP>::alloc);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    pdl_trigger();        // only after this CTA owns its tensor-memory columns (dependents allocate too)
     if (tid == 0) issue_layer_copy(raw, src, F, !train, false, &S.bar);
     const uint32_t t_g = S.tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(warp >> 2) * (GC + EC);
     const uint32_t t_e = t_g + GC;
@@ -498,7 +498,6 @@ __global__ void __launch_bounds__(kThreads, BwdDTmem<FP>::ctas_per_sm) k_bwd_lay
     src.sum1 = a.sum1 ? a.sum1 + (size_t)j * 4 * F : nullptr;
     src.n_total = a.n_total;
 
-    pdl_trigger();
     if (tid == 0) { mbar_init(&S.bar, 1); mbar_fence_init(); }
     if (warp == 0) tmem_alloc(&S.tmem_base, TM::alloc);
     if (tid < 12) S.corr[tid] = 0.f;
@@ -506,6 +505,7 @@ __global__ void __launch_bounds__(kThreads, BwdDTmem<FP>::ctas_per_sm) k_bwd_lay
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    pdl_trigger();        // only after this CTA owns its tensor-memory columns (dependents allocate too)
     const uint32_t t_acc = S.tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(warp >> 2) * TM::DC;
     if (tid == 0) issue_layer_copy(raw, src, F, !train, false, &S.bar);
     mbar_wait(&S.bar, 0u);

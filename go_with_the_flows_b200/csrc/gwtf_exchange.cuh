@@ -21,12 +21,13 @@ constexpr int kMaxRanks = 16;
 struct ExchangeArgs {
     int rank, world, n, slot;                 // n doubles to add up, slot = doubles per (parity, rank) slot
     unsigned long long seq;
+    unsigned long long timeout_ns;            // how long to wait for the peers before giving up
     double* data;                             // in: this rank's partial sums, out: the totals
     double* recv[kMaxRanks];                  // receive buffer of every rank: [2][world][slot] doubles
     unsigned long long* flags[kMaxRanks];     // flag array of every rank: [world]
 };
 
-__global__ void __launch_bounds__(256) k_exchange_sum(const ExchangeArgs a) {
+static __global__ void __launch_bounds__(256) k_exchange_sum(const ExchangeArgs a) {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the consumer's prologue may overlap the exchange
     asm volatile("griddepcontrol.wait;" ::: "memory");                // the producer's sums are complete
     const int tid = threadIdx.x;
@@ -46,7 +47,7 @@ __global__ void __launch_bounds__(256) k_exchange_sum(const ExchangeArgs a) {
         do {
             asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mine) : "memory");
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-            if (t1 - t0 > 20000000000ull) __trap();      // a peer never showed up (20 s): fail instead of hanging
+            if (t1 - t0 > a.timeout_ns) __trap();        // a peer never showed up: fail (sticky error) instead of hanging
         } while (v < a.seq);
     }
     __syncthreads();

@@ -136,7 +136,11 @@ __global__ void __launch_bounds__(kThreads) k_nll_eval(const EvalArgs a) {
 #pragma unroll
     for (int p = 0; p < P; ++p) {
         const int n = n0 + p * kThreads + tid;
-        if (valid[p]) a.nll[(size_t)b * N + n] = -(lse_m[p] + logf(lse_s[p]));
+        if (valid[p]) {
+            const float out = -(lse_m[p] + logf(lse_s[p]));
+            a.nll[(size_t)b * N + n] = out;
+            if (a.d.nonfinite && !isfinite(out)) atomicAdd(a.d.nonfinite, 1);
+        }
     }
 }
 
@@ -161,6 +165,11 @@ struct LayerArgs {
     double* sum1;           // (K,2,2,F)
     int B, N, tiles_per_shape;
     double n_total;
+    // segmented mode (sampling through the tcgen05 layer kernels): xin / xout are (B,3,N) rows in which the points
+    // that drew component j occupy [seg[j][b][0], + seg[j][b][1]) (segment starts are multiples of 128);
+    // seg_tiles[j][0..B] = exclusive prefix of the segments' 128-point tile counts.  Null = dense (K,B,3,N).
+    const int32_t* seg;
+    const int32_t* seg_tiles;
 };
 
 template <int FP>
@@ -323,7 +332,7 @@ __global__ void __launch_bounds__(kThreads) k_fwd_layer(const LayerArgs a) {
 }
 
 // moments of the raw data points (input of the first processed layer), replicated to K slots
-__global__ void __launch_bounds__(kThreads) k_moments(const float* __restrict__ pts, int B, int N, int K, double* mom) {
+static __global__ void __launch_bounds__(kThreads) k_moments(const float* __restrict__ pts, int B, int N, int K, double* mom) {
     __shared__ double dred[16];
     const int tid = threadIdx.x, lane = tid & 31;
     if (tid < 16) dred[tid] = 0.0;
@@ -348,7 +357,7 @@ __global__ void __launch_bounds__(kThreads) k_moments(const float* __restrict__ 
 
 // batch statistics actually used, for the running-stat update and for inspection
 // bstat [L][K][2][4][F]: mean0 | var0 | mean1 | var1
-__global__ void k_bstat(gwtf_stack_desc d, const float* params, const double* mom, const double* sum1, double n_total,
+static __global__ void k_bstat(gwtf_stack_desc d, const float* params, const double* mom, const double* sum1, double n_total,
                         float* bstat) {
     const int F = d.n_features, K = d.n_components, L = d.n_layers;
     const int total = L * K * 2 * F;
@@ -371,9 +380,10 @@ __global__ void k_bstat(gwtf_stack_desc d, const float* params, const double* mo
 }
 
 // per-point mixture NLL from the base-space samples (ubuf slot 0) and the log-det sums
-__global__ void __launch_bounds__(kThreads) k_nll_from_state(int K, int B, int N, const float* __restrict__ z,
+static __global__ void __launch_bounds__(kThreads) k_nll_from_state(int K, int B, int N, const float* __restrict__ z,
                                                              const float* __restrict__ ld, const float* __restrict__ base,
-                                                             const float* __restrict__ logw, float* nll, float* logp) {
+                                                             const float* __restrict__ logw, float* nll, float* logp,
+                                                             int32_t* nonfinite) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (size_t)B * N) return;
     const int b = (int)(i / N), n = (int)(i - (size_t)b * N);
@@ -391,7 +401,9 @@ __global__ void __launch_bounds__(kThreads) k_nll_from_state(int K, int B, int N
         const float v = lp + logw[b * K + j];
         if (v > m) { s = s * expf(m - v) + 1.0f; m = v; } else s += expf(v - m);
     }
-    nll[i] = -(m + logf(s));
+    const float out = -(m + logf(s));
+    nll[i] = out;
+    if (nonfinite && !isfinite(out)) atomicAdd(nonfinite, 1);      // training.py:43-46: the caller stops on a NaN loss
 }
 
 }  // namespace gwtf

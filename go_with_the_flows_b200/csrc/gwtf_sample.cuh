@@ -225,19 +225,34 @@ __global__ void __launch_bounds__(kThreads) k_sample(const SampleArgs a) {
 
 // =============================================================================================
 // Sampling through the per-layer tensor-core kernels.  The points of every shape are regrouped by
-// the component they drew -- (K, B, 3, Nmax) with Nmax = the largest per-(shape, component) count
-// rounded up to a tile -- pushed through the L direct layers with the same kernels the NLL passes
-// use (eval-mode BN, direct=1), and scattered back to their own slots.
+// the component they drew inside each shape's row -- (B, 3, Npad), Npad = roundup(N,128) + 128 K: component j's
+// points of shape b fill a segment that starts at a multiple of 128 -- pushed through the L direct layers with the
+// same kernels the NLL passes use (eval-mode BN, direct=1, segmented tiles), and gathered back to their own slots.
+// All sizes are upper bounds known before the draw: no host read-back anywhere.
 // =============================================================================================
 namespace gwtf {
+
+// Inclusive CDF of softmax(logits) per shape, the way np.random.choice builds it (flow_mixture.py:149-153):
+// fp32 probabilities e / sum(e) (sequential fp32 sum), float64 cumsum, normalised, stored fp32 with the last
+// entry pinned to 1.  e = fp32(exp(fp64(logit))) -- the correctly rounded fp32 exponential -- so that the
+// CPU restatement (oracle/flow_oracle.py: mixture_cdf) and this kernel agree bit for bit.
+static __global__ void k_mixture_cdf(const float* __restrict__ logits, int B, int K, float* cdf) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    float e[GWTF_MAX_COMPONENTS];
+    float sum = 0.f;
+    for (int j = 0; j < K; ++j) { e[j] = (float)exp((double)logits[(size_t)b * K + j]); sum += e[j]; }
+    double run = 0.0, c[GWTF_MAX_COMPONENTS];
+    for (int j = 0; j < K; ++j) { run += (double)(e[j] / sum); c[j] = run; }
+    for (int j = 0; j < K; ++j) cdf[(size_t)b * K + j] = j == K - 1 ? 1.0f : (float)(c[j] / run);
+}
 
 struct SamplePlanArgs {
     int K, B, N;
     const float* cdf;
     uint32_t seed_lo, stream_id;
     const int32_t* idx_in;
-    int32_t* counts;        // (B, K)
-    int32_t* nmax;          // running maximum over (b, j)
+    int32_t* counts;        // (B, K), pre-zeroed
 };
 
 __device__ __forceinline__ int sample_component(const float* cdf, int K, const int32_t* idx_in, int b, int n, int N,
@@ -248,78 +263,127 @@ __device__ __forceinline__ int sample_component(const float* cdf, int K, const i
     return c < 0 ? 0 : (c >= K ? K - 1 : c);
 }
 
-// one CTA per shape: how many points drew each component
-__global__ void __launch_bounds__(kThreads) k_sample_count(const SamplePlanArgs a) {
+constexpr int kSampleSpan = 16 * kThreads;      // points of one shape a count / scatter CTA covers
+
+// grid (ceil(N / kSampleSpan), B): how many points of each shape drew each component
+static __global__ void __launch_bounds__(kThreads) k_sample_count(const SamplePlanArgs a) {
     __shared__ int cnt[GWTF_MAX_COMPONENTS];
-    const int b = blockIdx.x, tid = threadIdx.x;
+    const int b = blockIdx.y, tid = threadIdx.x;
     if (tid < GWTF_MAX_COMPONENTS) cnt[tid] = 0;
     __syncthreads();
     const float* cdf = a.cdf + (size_t)b * a.K;
-    for (int n = tid; n < a.N; n += kThreads) {
+    const int n1 = min(a.N, (int)(blockIdx.x + 1) * kSampleSpan);
+    for (int n = blockIdx.x * kSampleSpan + tid; n < n1; n += kThreads) {
         uint4 w0;
         atomicAdd(&cnt[sample_component(cdf, a.K, a.idx_in, b, n, a.N, a.seed_lo, a.stream_id, w0)], 1);
     }
     __syncthreads();
-    if (tid < a.K) {
-        a.counts[b * a.K + tid] = cnt[tid];
-        atomicMax(a.nmax, cnt[tid]);
+    if (tid < a.K && cnt[tid]) atomicAdd(&a.counts[b * a.K + tid], cnt[tid]);
+}
+
+// one CTA: segment table seg[j][b] = (offset inside shape row b, count), segment starts rounded up to 128 points,
+// and seg_tiles[j][0..B] = exclusive prefix over shapes of the segments' tile counts; cursors zeroed.
+static __global__ void __launch_bounds__(kThreads) k_sample_plan(int K, int B, const int32_t* counts, int32_t* seg,
+                                                                 int32_t* seg_tiles, int32_t* cursor) {
+    const int tid = threadIdx.x;
+    for (int b = tid; b < B; b += kThreads) {
+        int off = 0;
+        for (int j = 0; j < K; ++j) {
+            const int c = counts[b * K + j];
+            seg[((size_t)j * B + b) * 2] = off;
+            seg[((size_t)j * B + b) * 2 + 1] = c;
+            cursor[b * K + j] = 0;
+            off += (c + 127) / 128 * 128;
+        }
+    }
+    __syncthreads();
+    if (tid < K) {
+        int run = 0;
+        for (int b = 0; b < B; ++b) {
+            seg_tiles[(size_t)tid * (B + 1) + b] = run;
+            run += (counts[b * K + tid] + 127) / 128;
+        }
+        seg_tiles[(size_t)tid * (B + 1) + B] = run;
     }
 }
 
 struct SampleScatterArgs {
-    int K, B, N, Nmax;
+    int K, B, N, Npad;
     const float *base, *cdf;
     uint32_t seed_lo, stream_id;
     const int32_t* idx_in;
     const float* eps_in;
-    float* xbuf;            // (K, B, 3, Nmax) base-space samples grouped by component (padding pre-zeroed)
-    int32_t* slot;          // (B, N): j * Nmax + position
+    const int32_t* seg;     // (K, B, 2)
+    int32_t* cursor;        // (B, K) running fill of every segment
+    float* xbuf;            // (B, 3, Npad) base-space samples, points grouped by component inside each row
+    int32_t* slot;          // (B, N): position of the point inside its row
     int32_t* labels;
     float* z_out;
 };
 
-// one CTA per shape: draw, place every point in its component's segment (order inside a segment is free)
-__global__ void __launch_bounds__(kThreads) k_sample_scatter(const SampleScatterArgs a) {
-    __shared__ int cursor[GWTF_MAX_COMPONENTS];
-    const int b = blockIdx.x, tid = threadIdx.x, N = a.N, K = a.K;
-    if (tid < GWTF_MAX_COMPONENTS) cursor[tid] = 0;
+// grid (ceil(N / kSampleSpan), B): draw, reserve a range of each component's segment for this CTA (one global atomic
+// per component), place the points (order inside a segment is free: results are gathered back by slot)
+static __global__ void __launch_bounds__(kThreads) k_sample_scatter(const SampleScatterArgs a) {
+    __shared__ int cnt[GWTF_MAX_COMPONENTS], start[GWTF_MAX_COMPONENTS];
+    const int b = blockIdx.y, tid = threadIdx.x, N = a.N, K = a.K;
+    if (tid < GWTF_MAX_COMPONENTS) cnt[tid] = 0;
     __syncthreads();
     float mub[3], sdb[3];
 #pragma unroll
     for (int d = 0; d < 3; ++d) { mub[d] = a.base[b * 6 + d]; sdb[d] = expf(0.5f * a.base[b * 6 + 3 + d]); }
     const float* cdf = a.cdf + (size_t)b * K;
-    for (int n = tid; n < N; n += kThreads) {
-        uint4 w0;
-        const int c = sample_component(cdf, K, a.idx_in, b, n, N, a.seed_lo, a.stream_id, w0);
+    constexpr int PER = kSampleSpan / kThreads;
+    int comp[PER], rank[PER];
+    const int nb = blockIdx.x * kSampleSpan;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+        const int n = nb + i * kThreads + tid;
+        comp[i] = -1;
+        if (n < N) {
+            uint4 w0;
+            comp[i] = sample_component(cdf, K, a.idx_in, b, n, N, a.seed_lo, a.stream_id, w0);
+            rank[i] = atomicAdd(&cnt[comp[i]], 1);
+        }
+    }
+    __syncthreads();
+    if (tid < K) start[tid] = cnt[tid] ? atomicAdd(&a.cursor[b * K + tid], cnt[tid]) : 0;
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+        const int n = nb + i * kThreads + tid;
+        if (comp[i] < 0) continue;
+        const int c = comp[i];
         float e[3];
         if (a.eps_in) {
 #pragma unroll
             for (int d = 0; d < 3; ++d) e[d] = a.eps_in[((size_t)b * 3 + d) * N + n];
         } else {
-            const uint4 w1 = philox4x32_10(make_uint4((uint32_t)n, (uint32_t)b, 1u, 0u), make_uint2(a.seed_lo, a.stream_id));
+            const uint2 key = make_uint2(a.seed_lo, a.stream_id);
+            const uint4 w0 = philox4x32_10(make_uint4((uint32_t)n, (uint32_t)b, 0u, 0u), key);
+            const uint4 w1 = philox4x32_10(make_uint4((uint32_t)n, (uint32_t)b, 1u, 0u), key);
             draw_normals(w0, w1, e);
         }
-        const int pos = atomicAdd(&cursor[c], 1);
+        const int pos = a.seg[((size_t)c * a.B + b) * 2] + start[c] + rank[i];
 #pragma unroll
         for (int d = 0; d < 3; ++d) {
             const float zv = fmaf(sdb[d], e[d], mub[d]);          // models.py:108: eps*std + mu
-            a.xbuf[(((size_t)c * a.B + b) * 3 + d) * a.Nmax + pos] = zv;
+            a.xbuf[((size_t)b * 3 + d) * a.Npad + pos] = zv;
             if (a.z_out) a.z_out[((size_t)b * 3 + d) * N + n] = zv;
         }
-        a.slot[(size_t)b * N + n] = c * a.Nmax + pos;
+        a.slot[(size_t)b * N + n] = pos;
         a.labels[(size_t)b * N + n] = c + 1;                      // flow_mixture.py:176
     }
 }
 
-__global__ void __launch_bounds__(kThreads) k_sample_gather(int B, int N, int Nmax, const float* xbuf, const int32_t* slot,
-                                                            float* samples) {
+static __global__ void __launch_bounds__(kThreads) k_sample_gather(int B, int N, int Npad, const float* xbuf,
+                                                                   const int32_t* slot, float* samples) {
     const size_t total = (size_t)B * N;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const int b = (int)(i / N), n = (int)(i - (size_t)b * N);
-        const int s = slot[i], j = s / Nmax, pos = s - j * Nmax;
+        const int pos = slot[i];
 #pragma unroll
         for (int d = 0; d < 3; ++d)
-            samples[((size_t)b * 3 + d) * N + n] = xbuf[(((size_t)j * B + b) * 3 + d) * Nmax + pos];
+            samples[((size_t)b * 3 + d) * N + n] = xbuf[((size_t)b * 3 + d) * Npad + pos];
     }
 }
 

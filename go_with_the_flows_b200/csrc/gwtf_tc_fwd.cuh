@@ -10,8 +10,9 @@
 //
 // A constant-one channel (index F) carries the biases through the chain, so the CUDA cores only do
 // relu + hi/lo split between the MMAs (3 instructions per channel, no shared-memory reads).
-//   CTA = 128 threads = 128 TMEM lanes (thread t owns point t of the tile); one tile in flight per
-//   CTA, 4 CTAs per SM (TMEM: [0,FPN) accumulator | [FPN,FPN+FPK) A hi | [FPN+FPK,FPN+2FPK) A lo).
+//   A warpgroup = 128 threads = 128 TMEM lanes (thread t owns point t of the tile); per tile slot the TMEM columns
+//   are [0,FPN) accumulator | [FPN,FPN+FPK) A hi | [FPN+FPK,FPN+2FPK) A lo.  The kernel that drives these
+//   building blocks is the persistent warp-specialised one in gwtf_tc_persist.cuh.
 #pragma once
 #include "gwtf_fwd.cuh"
 #include "gwtf_tc.cuh"
@@ -111,14 +112,15 @@ struct TcCols {
 };
 
 // one thread: D[128 x N] = A * B^T with the 3xTF32 passes, A from TMEM (hi/lo column blocks)
-template <int KT, int N>
+// PASSES = 3: fp32-grade 3xTF32; PASSES = 1: single-pass TF32 (the hi operands only)
+template <int KT, int N, int PASSES = 3>
 __device__ __forceinline__ void issue_ts(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, const float* b_hi,
                                          const float* b_lo) {
     const uint32_t idesc = make_idesc_tf32(128, N, 0, 0);
     const uint64_t bh = make_smem_desc_kmajor(b_hi, KT), bl = make_smem_desc_kmajor(b_lo, KT);
     bool acc = false;
 #pragma unroll
-    for (int pass = 0; pass < 3; ++pass) {
+    for (int pass = 0; pass < PASSES; ++pass) {
         const uint32_t a = pass == 1 ? a_lo : a_hi;
         const uint64_t b = pass == 2 ? bl : bh;
 #pragma unroll
@@ -150,7 +152,7 @@ __device__ __forceinline__ float* keep_ptr(float* keep, int j, int net, int F, i
     return keep + keep_slab(F, B, N, j, net) + ((p >> 4) * (size_t)(((F + 7) / 8) * 32) + (p & 7) * 4) * 4;
 }
 
-template <int FPK, int FPN>
+template <int FPK, int FPN, int PASSES = 3>
 __device__ __forceinline__ void relu_to_operand(uint32_t trow, float* keepf = nullptr, int keep_nt = 0, bool valid = true) {
     using C = TcCols<FPK, FPN>;
     float y[FPK];
@@ -174,6 +176,20 @@ __device__ __forceinline__ void relu_to_operand(uint32_t trow, float* keepf = nu
                 *reinterpret_cast<float4*>(keepf + (nt * 32 + t0 + (upper ? 1 : 0)) * 4) = out;
             }
         }
+    }
+    if (PASSES == 1) {
+        // single-pass TF32: the tensor core reads the top 19 bits of the fp32 word; round to nearest first so the
+        // error stays unbiased (relu + 2 integer ops per channel, one tcgen05.st instead of two)
+#pragma unroll
+        for (int c = 0; c < FPK; c += 8) {
+            float hi[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                hi[i] = __uint_as_float((__float_as_uint(fmaxf(y[c + i], 0.f)) + 0x1000u) & 0xffffe000u);
+            tmem_st8(trow + C::Ahi + c, hi);
+        }
+        tmem_wait_st();
+        return;
     }
 #pragma unroll
     for (int c = 0; c < FPK; c += 8) {
@@ -205,242 +221,6 @@ __device__ __forceinline__ void write_x_operand(float* x_hi, float* x_lo, const 
     const int off = kmajor_offset(tid, 0, 8);
     *reinterpret_cast<float4*>(x_hi + off) = make_float4(h[0], h[1], h[2], 1.0f);
     *reinterpret_cast<float4*>(x_lo + off) = make_float4(l[0], l[1], l[2], 0.0f);
-}
-
-template <int FPK, int FPN>
-struct TcFwdSmem {
-    LayerT<FPN> W;
-    TcLayerOps<FPK, FPN> ops[2];
-    float x_hi[128 * 8], x_lo[128 * 8];
-    uint64_t bar_tma, bar_mma;
-    uint32_t tmem_base;
-    float red[2][2 * FPN + 32];
-    double dred[16];
-};
-
-// MMA0 -> relu -> MMA1 for one net; on return y1 (phase 1) / h1 (phase 0) sits in TMEM columns [0,FPN)
-template <int FPK, int FPN>
-__device__ __forceinline__ void run_to_h1(TcFwdSmem<FPK, FPN>& S, int net, uint32_t tbase, uint32_t trow,
-                                          uint32_t& phase, int tid) {
-    using C = TcCols<FPK, FPN>;
-    if (tid == 0) {
-        tc_fence_after();
-        issue_ss_k8<FPN>(tbase + C::D, S.x_hi, S.x_lo, S.ops[net].B0.hi, S.ops[net].B0.lo);
-        tc_commit(&S.bar_mma);
-    }
-    tc_wait(&S.bar_mma, phase);
-    GWTF_RT(11);
-    relu_to_operand<FPK, FPN>(trow);
-    tc_handoff();
-    GWTF_RT(12);
-    if (tid == 0) {
-        tc_fence_after();
-        issue_ts<FPK, FPN>(tbase + C::D, tbase + C::Ahi, tbase + C::Alo, S.ops[net].B1.hi, S.ops[net].B1.lo);
-        tc_commit(&S.bar_mma);
-    }
-    tc_wait(&S.bar_mma, phase);
-}
-
-template <int FPK, int FPN, int PHASE>
-__global__ void __launch_bounds__(kTcThreads) k_fwd_layer_tc(const LayerArgs a) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    using SM = TcFwdSmem<FPK, FPN>;
-    using C = TcCols<FPK, FPN>;
-    SM& S = *reinterpret_cast<SM*>(smem_raw);
-    float* raw = reinterpret_cast<float*>(smem_raw + round_up((int)sizeof(SM), 16));
-    const int F = a.d.n_features, K = a.d.n_components, L = a.d.n_layers;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int j = blockIdx.y, l = a.layer;
-    const int N = a.N, B = a.B;
-    const bool train = a.train != 0;
-    constexpr int TT = kTcThreads;
-
-    LayerSrc src;
-    src.params = a.params + (size_t)(j * L + l) * a.d.rec_stride;
-    src.bn = a.bnbuf + (size_t)(j * L + l) * 8 * F;
-    src.film = nullptr;
-    src.mom = a.mom_in ? a.mom_in + j * GWTF_MOM_STRIDE : nullptr;
-    src.sum1 = a.sum1 ? a.sum1 + (size_t)j * 4 * F : nullptr;
-    src.n_total = a.n_total;
-
-    GWTF_T0();
-    if (warp == 0) tmem_alloc(&S.tmem_base, kTcCols);
-    if (tid == 0) { mbar_init(&S.bar_tma, 1); mbar_init(&S.bar_mma, 1); mbar_fence_init(); }
-    for (int i = tid; i < 2 * (2 * FPN + 32); i += TT) (&S.red[0][0])[i] = 0.f;
-    for (int i = tid; i < 128 * 8; i += TT) { S.x_hi[i] = 0.f; S.x_lo[i] = 0.f; }
-    if (tid < 16) S.dred[tid] = 0.0;
-    __syncthreads();
-    if (tid == 0) issue_layer_copy(raw, src, F, !train, false, &S.bar_tma);
-    mbar_wait(&S.bar_tma, 0u);
-    GWTF_T(0);
-    stage_vectors<FPN, false>(S.W, (LayerWB<FPN>*)nullptr, raw, src, F, a.d.warp_mask[l], train, PHASE == 0, nullptr,
-                              tid, TT);
-    __syncthreads();
-    GWTF_T(1);
-    const NetOffsets o = net_offsets(F, popc3(a.d.warp_mask[l]));
-#pragma unroll
-    for (int net = 0; net < 2; ++net) {
-        stage_b0<FPK, FPN>(S.ops[net], S.W.q0[net], F, tid, TT);
-        if (PHASE == 0) stage_b1<FPK, FPN>(S.ops[net], raw + net * o.stride + o.W1, nullptr, F, tid, TT);
-        else stage_b2<FPK, FPN>(S.ops[net], S.W.w2[net], S.W.b2[net], F, tid, TT);
-    }
-    fence_proxy_async();
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    GWTF_T(2);
-    const uint32_t tbase = S.tmem_base;
-    const uint32_t trow = tbase + ((uint32_t)(warp * 32) << 16);
-    uint32_t mma_phase = 0u;
-    float macc = 0.f;
-    int cur_b = -1;
-
-    // tiles of 128 points, never straddling shapes; a CTA takes a CONTIGUOUS range so that it
-    // re-stages the per-shape B1 operand only when it crosses a shape boundary
-    const int total_tiles = B * a.tiles_per_shape;
-    const int per_cta = (total_tiles + gridDim.x - 1) / gridDim.x;
-    const int t_begin = blockIdx.x * per_cta, t_end = min(t_begin + per_cta, total_tiles);
-    float mv[9];                                       // per-thread moment partials of the outputs
-#pragma unroll
-    for (int i = 0; i < 9; ++i) mv[i] = 0.f;
-    // software prefetch: the next tile's coordinates (and running log-det sums) are loaded while the
-    // current tile is in the MMA chain, so their global latency is off the critical path
-    auto tile_coords = [&](int t, int& b, int& n, bool& valid) {
-        b = t / a.tiles_per_shape;
-        n = (t - b * a.tiles_per_shape) * TT + tid;
-        valid = n < N;
-    };
-    auto load_x = [&](int t, float (&x)[3], float (&s3)[3]) {
-        int b, n; bool valid;
-        tile_coords(t, b, n, valid);
-        const float* xin = a.xin_shared ? a.xin + (size_t)b * 3 * N : a.xin + ((size_t)j * B + b) * 3 * N;
-#pragma unroll
-        for (int d = 0; d < 3; ++d) {
-            x[d] = valid ? xin[(size_t)d * N + n] : 0.f;
-            s3[d] = (PHASE == 1 && a.ssum && valid) ? a.ssum[((size_t)j * B + b) * 3 * N + (size_t)d * N + n] : 0.f;
-        }
-    };
-    float xn[3], sn[3];
-    if (t_begin < t_end) load_x(t_begin, xn, sn);
-    for (int t = t_begin; t < t_end; ++t) {
-        int b, n; bool valid;
-        tile_coords(t, b, n, valid);
-        if (PHASE == 1 && b != cur_b) {
-            __syncthreads();
-            stage_film<FPN, false>(S.W, (LayerWB<FPN>*)nullptr, a.film + ((size_t)(b * K + j) * L + l) * 4 * F, F, tid,
-                                   TT);
-            __syncthreads();
-#pragma unroll
-            for (int net = 0; net < 2; ++net)
-                stage_b1<FPK, FPN>(S.ops[net], raw + net * o.stride + o.W1, S.W.st[net], F, tid, TT);
-            cur_b = b;
-            GWTF_T(3);
-        }
-        float x[3], s3[3];
-#pragma unroll
-        for (int d = 0; d < 3; ++d) { x[d] = xn[d]; s3[d] = sn[d]; }
-        write_x_operand(S.x_hi, S.x_lo, x, tid);
-        fence_proxy_async();
-        tc_handoff();
-        GWTF_T(4);
-        if (t + 1 < t_end) load_x(t + 1, xn, sn);
-
-        if (PHASE == 0) {
-#pragma unroll 1
-            for (int net = 0; net < 2; ++net) {
-                run_to_h1<FPK, FPN>(S, net, tbase, trow, mma_phase, tid);
-                GWTF_T(5);
-                // per-channel sum h1, sum h1^2: 16 channels -> 32 values per warp reduce-scatter
-                float h[FPN];
-                tmem_ld<FPN>(trow + C::D, h);
-                tmem_wait_ld();
-#pragma unroll
-                for (int c = 0; c < FPN; c += 16) {
-                    float v[32];
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const float hv = valid ? h[c + i] : 0.f;
-                        v[2 * i] = hv;
-                        v[2 * i + 1] = hv * hv;
-                    }
-                    const float r = warp_reduce_scatter32(v, lane);
-                    atomicAdd(&S.red[net][2 * c + lane], r);
-                }
-                tc_handoff();      // every thread is done with the accumulator before the next MMA0
-                GWTF_T(6);
-            }
-        } else {
-            float o3[2][3];
-#pragma unroll 1
-            for (int net = 0; net < 2; ++net) {
-                run_to_h1<FPK, FPN>(S, net, tbase, trow, mma_phase, tid);
-                GWTF_T(5);
-                relu_to_operand<FPK, FPN>(trow, keep_ptr(a.y1out, j, net, F, B, N, b, n), (F + 7) / 8, valid);
-                tc_handoff();
-                GWTF_T(7);
-                if (tid == 0) {
-                    tc_fence_after();
-                    issue_ts<FPK, 16>(tbase + C::D, tbase + C::Ahi, tbase + C::Alo, S.ops[net].B2.hi, S.ops[net].B2.lo);
-                    tc_commit(&S.bar_mma);
-                }
-                tc_wait(&S.bar_mma, mma_phase);
-                GWTF_T(8);
-                float ov[8];
-                tmem_ld8(trow + C::D, ov);
-                tmem_wait_ld();
-                o3[net][0] = ov[0]; o3[net][1] = ov[1]; o3[net][2] = ov[2];
-                tc_handoff();
-                GWTF_T(9);
-            }
-            float lam[3];
-            if (a.direct) warp_point<true>(x, o3[0], o3[1], lam);
-            else warp_point<false>(x, o3[0], o3[1], lam);
-            if (valid) {
-                const size_t base = ((size_t)j * B + b) * 3 * N + n;
-#pragma unroll
-                for (int d = 0; d < 3; ++d) a.xout[base + (size_t)d * N] = x[d];
-                if (a.ld) a.ld[((size_t)j * B + b) * N + n] += lam[0] + lam[1] + lam[2];
-                if (a.ssum)
-#pragma unroll
-                    for (int d = 0; d < 3; ++d) a.ssum[base + (size_t)d * N] = s3[d] + lam[d];
-                if (a.trio) {
-                    const size_t tb = (((size_t)j * 3) * B + b) * 3 * N + n;
-                    const size_t ts = (size_t)B * 3 * N;
-#pragma unroll
-                    for (int d = 0; d < 3; ++d) {
-                        a.trio[tb + (size_t)d * N] = x[d];
-                        a.trio[tb + ts + (size_t)d * N] = o3[0][d];
-                        a.trio[tb + 2 * ts + (size_t)d * N] = lam[d];
-                    }
-                }
-                mv[0] += x[0]; mv[1] += x[1]; mv[2] += x[2];
-                mv[3] += x[0] * x[0]; mv[4] += x[0] * x[1]; mv[5] += x[0] * x[2];
-                mv[6] += x[1] * x[1]; mv[7] += x[1] * x[2]; mv[8] += x[2] * x[2];
-            }
-            GWTF_T(10);
-        }
-    }
-    if (PHASE == 1 && a.mom_out) {
-        float v[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = i < 9 ? mv[i] : 0.f;
-        macc = warp_reduce_scatter32(v, lane);
-    }
-    // ---- flush block partials
-    __syncthreads();
-    if (PHASE == 0) {
-        for (int i = tid; i < 2 * 2 * FPN; i += TT) {
-            const int net = i / (2 * FPN), idx = i - net * 2 * FPN, f = idx >> 1, which = idx & 1;
-            if (f < F) atomicAdd(&a.sum1[((size_t)j * 2 + net) * 2 * F + which * F + f], (double)S.red[net][idx]);
-        }
-    } else if (a.mom_out) {
-        if (lane < 9) atomicAdd(&S.dred[lane], (double)macc);
-        __syncthreads();
-        if (tid < 9) atomicAdd(&a.mom_out[j * GWTF_MOM_STRIDE + tid], S.dred[tid]);
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 0) tmem_dealloc(tbase, kTcCols);
 }
 
 }  // namespace gwtf

@@ -46,23 +46,36 @@ struct TcPersistSmem {
     double dred[16];
 };
 
-// the CTA's contiguous tile range cut into rounds of <= kSlots tiles that never straddle a shape
+// the CTA's contiguous tile range cut into rounds of <= kSlots tiles that never straddle a shape.  Dense mode:
+// every shape has `tps` tiles; segmented mode: shape b of this component owns tiles [pre[b], pre[b+1]).
 struct RoundIter {
     int t, t_end, tps;
-    __device__ __forceinline__ bool next(int& base, int& count, int& b) {
+    const int32_t* pre;          // null = dense
+    int b, s_begin, s_end;
+    __device__ __forceinline__ RoundIter(int t0, int t1, int tps_, const int32_t* pre_, int B) : t(t0), t_end(t1), tps(tps_), pre(pre_) {
+        if (!pre) { b = t0 / tps; s_begin = b * tps; s_end = s_begin + tps; return; }
+        int lo = 0, hi = B;                  // largest b with pre[b] <= t0
+        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (pre[mid] <= t0) lo = mid; else hi = mid; }
+        b = lo; s_begin = pre[lo]; s_end = pre[lo + 1];
+    }
+    __device__ __forceinline__ bool next(int& base, int& count, int& bb) {
         if (t >= t_end) return false;
-        b = t / tps;
-        const int ti = t - b * tps;
-        int end = b * tps + min(tps, (ti / kSlots + 1) * kSlots);
+        while (t >= s_end) { ++b; s_begin = s_end; s_end = pre ? pre[b + 1] : s_end + tps; }
+        const int ti = t - s_begin;
+        int end = s_begin + min(s_end - s_begin, (ti / kSlots + 1) * kSlots);
         end = min(end, t_end);
         base = t;
         count = end - t;
+        bb = b;
         t = end;
         return true;
     }
+    __device__ __forceinline__ int shape_begin() const { return s_begin; }
 };
 
-template <int FPK, int FPN, int PHASE>
+// PASSES: 3 = fp32-grade 3xTF32 (training, anything that feeds gradients), 1 = single-pass TF32 for the
+// no-grad eval-mode NLL and the sampling pass (gwtf_stack_desc.eval_precision)
+template <int FPK, int FPN, int PHASE, int PASSES = 3>
 __global__ void __launch_bounds__(kPersistThreads, 1) k_fwd_layer_tcp(const LayerArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     using SM = TcPersistSmem<FPK, FPN>;
@@ -88,7 +101,6 @@ __global__ void __launch_bounds__(kPersistThreads, 1) k_fwd_layer_tcp(const Laye
     src.sum1 = a.sum1 ? a.sum1 + (size_t)j * 4 * F : nullptr;
     src.n_total = a.n_total;
 
-    pdl_trigger();
     if (warp == kSlots * 4) tmem_alloc(&S.tmem_base, 512);
     if (tid == 0) {
         mbar_init(&S.bar_tma, 1);
@@ -99,6 +111,9 @@ __global__ void __launch_bounds__(kPersistThreads, 1) k_fwd_layer_tcp(const Laye
     for (int i = tid; i < kSlots * 128 * 8; i += kPersistThreads) { (&S.x_hi[0][0])[i] = 0.f; (&S.x_lo[0][0])[i] = 0.f; }
     if (tid < 16) S.dred[tid] = 0.0;
     __syncthreads();
+    // dependents may start launching only now: their CTAs allocate tensor memory too, and a CTA of THIS grid that
+    // had triggered before its own tcgen05.alloc could starve behind them
+    pdl_trigger();
     if (tid == 0) issue_layer_copy(raw, src, F, !train, false, &S.bar_tma);
     mbar_wait(&S.bar_tma, 0u);
     const NetOffsets o = net_offsets(F, popc3(a.d.warp_mask[l]));
@@ -122,7 +137,8 @@ __global__ void __launch_bounds__(kPersistThreads, 1) k_fwd_layer_tcp(const Laye
     tc_fence_after();
     const uint32_t tbase = S.tmem_base;
 
-    const int total_tiles = B * a.tiles_per_shape;
+    const int32_t* pre = a.seg_tiles ? a.seg_tiles + (size_t)j * (B + 1) : nullptr;
+    const int total_tiles = pre ? pre[B] : B * a.tiles_per_shape;
     const int per_cta = (total_tiles + gridDim.x - 1) / gridDim.x;
     const int t_begin = min(blockIdx.x * per_cta, total_tiles), t_end = min(t_begin + per_cta, total_tiles);
 
@@ -132,7 +148,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) k_fwd_layer_tcp(const Laye
         if (lane == 0) {
             int remaining = 0;
             {
-                RoundIter it{t_begin, t_end, a.tiles_per_shape};
+                RoundIter it(t_begin, t_end, a.tiles_per_shape, pre, B);
                 int base, count, b;
                 while (it.next(base, count, b)) remaining += (s < count) ? STAGES : 0;
             }
@@ -145,8 +161,8 @@ __global__ void __launch_bounds__(kPersistThreads, 1) k_fwd_layer_tcp(const Laye
                 tc_fence_after();
                 const int net = st / (STAGES / 2), k = st - net * (STAGES / 2);
                 if (k == 0) issue_ss_k8<FPN>(tslot + C::D, S.x_hi[s], S.x_lo[s], S.ops[net].B0.hi, S.ops[net].B0.lo);
-                else if (k == 1) issue_ts<FPK, FPN>(tslot + C::D, tslot + C::Ahi, tslot + C::Alo, S.ops[net].B1.hi, S.ops[net].B1.lo);
-                else issue_ts<FPK, 16>(tslot + C::D, tslot + C::Ahi, tslot + C::Alo, S.ops[net].B2.hi, S.ops[net].B2.lo);
+                else if (k == 1) issue_ts<FPK, FPN, PASSES>(tslot + C::D, tslot + C::Ahi, tslot + C::Alo, S.ops[net].B1.hi, S.ops[net].B1.lo);
+                else issue_ts<FPK, 16, PASSES>(tslot + C::D, tslot + C::Ahi, tslot + C::Alo, S.ops[net].B2.hi, S.ops[net].B2.lo);
                 tc_commit(&S.done[s]);
                 st = st + 1 == STAGES ? 0 : st + 1;
                 --remaining;
@@ -165,7 +181,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) k_fwd_layer_tcp(const Laye
 #pragma unroll
         for (int i = 0; i < 9; ++i) mv[i] = 0.f;
         int cur_b = -1;
-        RoundIter it{t_begin, t_end, a.tiles_per_shape};
+        RoundIter it(t_begin, t_end, a.tiles_per_shape, pre, B);
         int base, count, b;
         while (it.next(base, count, b)) {
             if (PHASE == 1 && b != cur_b) {
@@ -182,10 +198,16 @@ __global__ void __launch_bounds__(kPersistThreads, 1) k_fwd_layer_tcp(const Laye
             }
             if (slot >= count) continue;
             const int t = base + slot;
-            const int n = (t - b * a.tiles_per_shape) * 128 + wtid;
-            const bool valid = n < N;
+            int n = (t - it.shape_begin()) * 128 + wtid;
+            bool valid = n < N;
+            if (a.seg) {                                            // segmented rows: (offset, count) of (j, b)
+                const int2 sg = *reinterpret_cast<const int2*>(a.seg + ((size_t)j * B + b) * 2);
+                valid = n < sg.y;
+                n += sg.x;
+            }
             float x[3], s3[3];
-            const float* xin = a.xin_shared ? a.xin + (size_t)b * 3 * N : a.xin + ((size_t)j * B + b) * 3 * N;
+            const bool shared_rows = a.xin_shared || a.seg;
+            const float* xin = shared_rows ? a.xin + (size_t)b * 3 * N : a.xin + ((size_t)j * B + b) * 3 * N;
 #pragma unroll
             for (int d = 0; d < 3; ++d) {
                 x[d] = valid ? xin[(size_t)d * N + n] : 0.f;
@@ -198,7 +220,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) k_fwd_layer_tcp(const Laye
 #pragma unroll 1
                 for (int net = 0; net < 2; ++net) {
                     wait_done();                                    // y0
-                    relu_to_operand<FPK, FPN>(trow);
+                    relu_to_operand<FPK, FPN, PASSES>(trow);
                     request();                                      // -> MMA1
                     wait_done();                                    // h1
                     float h[FPN];
@@ -223,10 +245,10 @@ __global__ void __launch_bounds__(kPersistThreads, 1) k_fwd_layer_tcp(const Laye
 #pragma unroll 1
                 for (int net = 0; net < 2; ++net) {
                     wait_done();                                    // y0
-                    relu_to_operand<FPK, FPN>(trow);
+                    relu_to_operand<FPK, FPN, PASSES>(trow);
                     request();                                      // -> MMA1
                     wait_done();                                    // y1
-                    relu_to_operand<FPK, FPN>(trow, keep_ptr(a.y1out, j, net, F, B, N, b, n), (F + 7) / 8, valid);
+                    relu_to_operand<FPK, FPN, PASSES>(trow, keep_ptr(a.y1out, j, net, F, B, N, b, n), (F + 7) / 8, valid);
                     request();                                      // -> MMA2
                     wait_done();                                    // o
                     float ov[8];
@@ -239,7 +261,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) k_fwd_layer_tcp(const Laye
                 if (a.direct) warp_point<true>(x, o3[0], o3[1], lam);
                 else warp_point<false>(x, o3[0], o3[1], lam);
                 if (valid) {
-                    const size_t gb = ((size_t)j * B + b) * 3 * N + n;
+                    const size_t gb = (a.seg ? (size_t)b : (size_t)j * B + b) * 3 * N + n;
 #pragma unroll
                     for (int d = 0; d < 3; ++d) a.xout[gb + (size_t)d * N] = x[d];
                     if (a.ld) a.ld[((size_t)j * B + b) * N + n] += lam[0] + lam[1] + lam[2];

@@ -38,24 +38,53 @@ def _world():
     return 1
 
 
-_PEER = {'state': None, 'keep': None}     # process-wide peer-memory statistic exchange (see gwtf.h)
+def _env_int(name, default):
+    import os
+    v = os.environ.get(name)
+    try:
+        return int(v) if v not in (None, '') else default
+    except ValueError:
+        return default
+
+
+# Execution options new FlowStacks start with (they live in each stack's descriptor, not in the library):
+#   engine          GWTF_ENGINE = 4 tcgen05 forward + backward (default) | 2 tcgen05 forward + mma.sync backward |
+#                   3 mma.sync | 0 FP32 FMA
+#   pdl             GWTF_PDL = 1 programmatic dependent launch of the layer kernels (default) | 0
+#   eval_precision  GWTF_EVAL_PRECISION = 0 fp32-grade 3xTF32 | 1 single-pass TF32 for the no-grad eval-mode NLL and
+#                   the sampling pass
+_DEFAULTS = {'engine': _env_int('GWTF_ENGINE', nat.ENGINE_TC), 'pdl': _env_int('GWTF_PDL', 1),
+             'eval_precision': _env_int('GWTF_EVAL_PRECISION', nat.PRECISION_3XTF32)}
+
+
+def set_default(name, value):
+    """Set an execution option for FlowStacks created from now on; returns the previous value."""
+    prev = _DEFAULTS[name]
+    _DEFAULTS[name] = value
+    return prev
+
+
+_PEER = {'state': None, 'keep': None, 'handle': None}     # process-wide peer-memory statistic exchange (see gwtf.h)
 
 
 def peer_exchange(slot_doubles, dev):
-    """Attach the NVLink peer-memory statistic exchange (csrc/gwtf_exchange.cuh) once per process: a
+    """Create the NVLink peer-memory statistic exchange (csrc/gwtf_exchange.cuh) once per process group: a
     symmetric-memory buffer per rank holding the flag array and the double-buffered receive slots.
-    Returns True when the exchange is usable, False when the ranks should fall back to NCCL all-reduces
+    Returns the exchange handle (int) when usable, None when the ranks should fall back to NCCL all-reduces
     of the statistic arrays (CPU/gloo groups, GWTF_PEER_EXCHANGE=0, no symmetric memory)."""
     import os
     st = _PEER['state']
     if _PEER.get('group') != (dist.get_world_size(), dist.get_rank()):
+        if _PEER['handle']:
+            nat.lib().gwtf_exchange_destroy(ctypes.c_void_p(_PEER['handle']))
         st = _PEER['state'] = None                  # a new process group: attach again
+        _PEER['handle'] = None
         _PEER['group'] = (dist.get_world_size(), dist.get_rank())
     if st is not None and (st is False or st >= slot_doubles):
-        return bool(st)
+        return _PEER['handle'] if st else None
     if os.environ.get('GWTF_PEER_EXCHANGE', '1') == '0' or dist.get_backend() != 'nccl':
         _PEER['state'] = False
-        return False
+        return None
     world, rank = dist.get_world_size(), dist.get_rank()
     ok = torch.ones(1, device=dev)
     try:
@@ -74,14 +103,20 @@ def peer_exchange(slot_doubles, dev):
     dist.all_reduce(ok, op=dist.ReduceOp.MIN)
     if float(ok.item()) < 1.0:
         _PEER['state'] = False
-        return False
+        return None
     arr = ctypes.c_void_p * world
     recv = arr(*[ctypes.c_void_p(q + head * 8) for q in ptrs])
     flags = arr(*[ctypes.c_void_p(q) for q in ptrs])
-    nat.check(nat.lib().gwtf_exchange_attach(rank, world, recv, flags, slot), 'gwtf_exchange_attach')
+    out = ctypes.c_void_p()
+    if _PEER['handle']:
+        nat.lib().gwtf_exchange_destroy(ctypes.c_void_p(_PEER['handle']))
+    timeout = float(os.environ.get('GWTF_EXCHANGE_TIMEOUT_S', '600'))
+    nat.check(nat.lib().gwtf_exchange_create(rank, world, recv, flags, slot, timeout, ctypes.byref(out)),
+              'gwtf_exchange_create')
     _PEER['state'] = slot
     _PEER['keep'] = (buf, hdl)
-    return True
+    _PEER['handle'] = out.value
+    return out.value
 
 
 class _LayerRef:
@@ -176,14 +211,19 @@ class FlowStack:
             for d in warp:
                 mask |= 1 << d
             self.desc.warp_mask[l] = mask
+        self.desc.engine = _DEFAULTS['engine']
+        self.desc.flags = 0 if _DEFAULTS['pdl'] else nat.FLAG_NO_PDL
+        self.desc.eval_precision = _DEFAULTS['eval_precision']
+        self.desc.exchange = None
+        self.desc.nonfinite = None
+        self._nonfinite = None       # device counter of non-finite per-point NLLs (training.py:43-46 stop condition)
         self.sync_gradients = True
         self._n_total_cache = {}
-        # keep the sd1 output of every layer/net from the forward apply pass so that the backward phases
+        # keep the sd1 output of every layer/net from the forward apply pass so that the mma.sync backward phases
         # skip one F x F contraction each (320 B per point/component/layer at F=37: 5.5 GB for 64 x 2048
-        # points).  None = automatic: on for the tensor-core engines (fragment-ordered buffer, coalesced
-        # 16-byte accesses), off for the FMA engine where recomputing measured faster (r01: 309/429 us vs
-        # 214/380 us per backward launch)
-        self.keep_activations = None
+        # points).  Off by default: the backward recomputes from the 12-byte layer inputs (the tcgen05 backward
+        # always does); True trades 20 GB of HBM traffic per step for ~6 % on the mma.sync engines.
+        self.keep_activations = False
         self._keep_pool = {}
         self.C = self.K * self.L * 4
         if self.flat:
@@ -280,6 +320,8 @@ class FlowStack:
                     owner._buffers[attr] = view
             if name in self.grad_masters:
                 ms.params = [ms.current(m) for m in ms.members]
+                for prm in ms.params:              # lets the optimizer update the whole master in one kernel
+                    prm._gwtf_master = ms
                 flat.requires_grad_(True)
                 flat.register_hook(self._make_reduce_hook())
                 flat.register_post_accumulate_grad_hook(self._make_attach_hook(ms))
@@ -418,7 +460,7 @@ class FlowStack:
         nbt[:, :, :2] += 1
 
     # ------------------------------------------------------------------ FiLM nets
-    def film(self, g, training, sync):
+    def film(self, g, training, sync, update_stats=True):
         """(B,K,L,2,2,F): [...,0,:] = eps + exp(cond_w(g)), [...,1,:] = cond_b(g)."""
         K, L, Fd, C = self.K, self.L, self.F, self.C
         T = self._cond_tensors()
@@ -428,7 +470,9 @@ class FlowStack:
         if training:
             Hn, mean, var_unb = _batch_norm_train(H, bw, bb, sync)
             with torch.no_grad():
-                if self.flat:
+                if not update_stats:
+                    pass
+                elif self.flat:
                     rm.lerp_(mean, BN_MOMENTUM)
                     rv.lerp_(var_unb, BN_MOMENTUM)
                     self.masters['nbt'].tensor.view(K * L, 2, 4)[:, :, 2:] += 1
@@ -461,6 +505,37 @@ class FlowStack:
             self.update_point_bn(bstat, n_total)
         return z, ssum
 
+    # ------------------------------------------------------------------ options / diagnostics
+    def fwd_engine(self):
+        return int(nat.lib().gwtf_resolved_engine(ctypes.byref(self.desc), 0))
+
+    def bwd_engine(self):
+        return int(nat.lib().gwtf_resolved_engine(ctypes.byref(self.desc), 1))
+
+    def nonfinite_counter(self, dev):
+        """int32 device counter the NLL kernels bump for every non-finite per-point NLL they write."""
+        if self._nonfinite is None or self._nonfinite.device != dev:
+            self._nonfinite = torch.zeros(1, dtype=torch.int32, device=dev)
+            self.desc.nonfinite = self._nonfinite.data_ptr()
+        return self._nonfinite
+
+    def take_nonfinite(self):
+        """Number of non-finite per-point NLLs since the last call (one 4-byte read-back); the reference's
+        loop stops without an optimizer step when the loss is NaN (training.py:43-46)."""
+        if self._nonfinite is None:
+            return 0
+        n = int(self._nonfinite.item())
+        if n:
+            self._nonfinite.zero_()
+        return n
+
+    def _scratch(self, key, nbytes, dev):
+        """Stream-ordered scratch reused across calls of the same shape (never handed to autograd)."""
+        buf = self._keep_pool.get(key)
+        if buf is None or buf.numel() < nbytes or buf.device != dev:
+            buf = self._keep_pool[key] = torch.empty(int(nbytes), dtype=torch.uint8, device=dev)
+        return buf
+
     @torch.no_grad()
     def nll_eval_fused(self, p, g, base, logw, want_logp=False):
         """Fused no-grad eval forward -> nll (B,N) [, logp (B,N,K)]."""
@@ -472,20 +547,22 @@ class FlowStack:
         B, _, N = p.shape
         nll = torch.empty(B, N, device=p.device)
         logp = torch.empty(B, N, self.K, device=p.device) if want_logp else None
-        if nat.lib().gwtf_engine() != 0:
+        self.nonfinite_counter(p.device)
+        desc = ctypes.byref(self.desc)
+        lib = nat.lib()
+        if self.fwd_engine() != nat.ENGINE_FMA:
             # per-layer tensor-core kernels (L launches, two ping-pong slots): faster than the single-launch
             # FMA kernel at every size measured (64 x 2048: 2.2 vs 3.3 ms; 4 x 2048: 0.5 vs 3.3 ms)
-            scratch = torch.empty(2, self.K, B, 3, N, device=p.device)
-            ld = torch.empty(self.K, B, N, device=p.device)
-            nat.check(nat.lib().gwtf_nll_fwd_eval_layers(ctypes.byref(self.desc), nat.ptr(params), nat.ptr(bnbuf),
-                                                         nat.ptr(film), nat.ptr(p), nat.ptr(base.contiguous()),
-                                                         nat.ptr(logw.contiguous()), nat.ptr(scratch), nat.ptr(ld), B, N,
-                                                         nat.ptr(nll), nat.ptr(logp), _stream_ptr()),
+            need = int(lib.gwtf_eval_layers_workspace_bytes(desc, B, N))
+            ws = self._scratch('eval_ws', need, p.device)
+            nat.check(lib.gwtf_nll_fwd_eval_layers(desc, nat.ptr(params), nat.ptr(bnbuf), nat.ptr(film), nat.ptr(p),
+                                                   nat.ptr(base.contiguous()), nat.ptr(logw.contiguous()), nat.ptr(ws),
+                                                   need, B, N, nat.ptr(nll), nat.ptr(logp), _stream_ptr()),
                       'gwtf_nll_fwd_eval_layers')
             return (nll, logp) if want_logp else nll
-        nat.check(nat.lib().gwtf_nll_fwd_eval(ctypes.byref(self.desc), nat.ptr(params), nat.ptr(bnbuf), nat.ptr(film),
-                                              nat.ptr(p), nat.ptr(base.contiguous()), nat.ptr(logw.contiguous()),
-                                              B, N, nat.ptr(nll), nat.ptr(logp), None, None, _stream_ptr()),
+        nat.check(lib.gwtf_nll_fwd_eval(desc, nat.ptr(params), nat.ptr(bnbuf), nat.ptr(film),
+                                        nat.ptr(p), nat.ptr(base.contiguous()), nat.ptr(logw.contiguous()),
+                                        B, N, nat.ptr(nll), nat.ptr(logp), None, None, _stream_ptr()),
                   'gwtf_nll_fwd_eval')
         return (nll, logp) if want_logp else nll
 
@@ -553,15 +630,14 @@ class _StackNLLPass(torch.autograd.Function):
         desc = ctypes.byref(stack.desc)
         st = _stream_ptr()
         ubuf = torch.empty(L, K, B, 3, N, device=dev)
-        ssum = torch.zeros(K, B, 3, N, device=dev)
-        ld = torch.zeros(K, B, N, device=dev)
+        ssum = torch.empty(K, B, 3, N, device=dev)      # (the drivers zero what they accumulate into)
+        ld = torch.empty(K, B, N, device=dev)
         mom = sum1 = bstat = None
         n_total = float(B * N)
         # activations kept for backward (layout private to the engine, sized by the library)
         ybuf = None
-        keep = stack.keep_activations
-        if keep is None:
-            keep = lib.gwtf_engine() != 0 and any(ctx.needs_input_grad)
+        keep = bool(stack.keep_activations) and any(ctx.needs_input_grad) and \
+            int(lib.gwtf_keep_floats(desc, B, N)) > 0
         if keep:
             # multi-GB scratch: recycled through a per-stack pool (returned by backward) so that the
             # caching allocator never splits or re-mallocs it between steps
@@ -574,10 +650,11 @@ class _StackNLLPass(torch.autograd.Function):
                 if 4 * need < 0.5 * free + torch.cuda.memory_reserved(dev) - torch.cuda.memory_allocated(dev):
                     ybuf = torch.empty(need, device=dev)
         if training:
-            mom = torch.zeros(L, K, nat.MOM_STRIDE, device=dev, dtype=torch.float64)
-            sum1 = torch.zeros(L, K, 2, 2, Fd, device=dev, dtype=torch.float64)
+            mom = torch.empty(L, K, nat.MOM_STRIDE, device=dev, dtype=torch.float64)
+            sum1 = torch.empty(L, K, 2, 2, Fd, device=dev, dtype=torch.float64)
             bstat = torch.empty(L, K, 2, 4, Fd, device=dev)
-        peer = sync and peer_exchange(K * 8 * Fd, dev)
+        peer = peer_exchange(K * 8 * Fd, dev) if sync else None
+        stack.desc.exchange = peer
         if not sync:
             nat.check(lib.gwtf_fwd_all(desc, int(training), nat.ptr(params), nat.ptr(bnbuf), nat.ptr(film), nat.ptr(p),
                                        None, None, nat.ptr(ubuf), nat.ptr(ld), nat.ptr(ssum), nat.ptr(ybuf), nat.ptr(mom),
@@ -591,6 +668,10 @@ class _StackNLLPass(torch.autograd.Function):
                       'gwtf_fwd_all_ranks')
         else:
             n_total = stack.global_points(B, N, dev)
+            ssum.zero_()
+            ld.zero_()
+            mom.zero_()
+            sum1.zero_()
             nat.check(lib.gwtf_fwd_moments(desc, nat.ptr(p), B, N, nat.ptr(mom[L - 1]), st), 'gwtf_fwd_moments')
             for l in range(L - 1, -1, -1):
                 dist.all_reduce(mom[l])
@@ -605,7 +686,7 @@ class _StackNLLPass(torch.autograd.Function):
         ctx.stack = stack
         ctx.training = training
         ctx.sync = sync
-        ctx.peer = bool(peer)
+        ctx.peer = peer is not None
         ctx.n_total = n_total
         # running stats are updated in place right after a train-mode forward (and are not read by
         # the train-mode backward), so they must not go through save_for_backward's version check
@@ -631,9 +712,10 @@ class _StackNLLPass(torch.autograd.Function):
         gbuf = dz.contiguous().clone() if dz is not None else torch.zeros(K, B, 3, N, device=dev)
         gs = dssum.contiguous() if dssum is not None else torch.zeros(K, B, 3, N, device=dev)
         dobuf = torch.empty(K, B, 6, N, device=dev)
-        dparams = torch.zeros_like(params)
-        dfilm = torch.zeros_like(film)
-        dpoints = torch.zeros_like(p)
+        acc = torch.zeros(params.numel() + film.numel() + p.numel(), device=dev)      # one memset for the three
+        dparams = acc[:params.numel()].view_as(params)
+        dfilm = acc[params.numel():params.numel() + film.numel()].view_as(film)
+        dpoints = acc[params.numel() + film.numel():].view_as(p)
         bsum = torch.zeros(L, K, 2, 4, Fd, device=dev, dtype=torch.float64)
         train = int(ctx.training)
         if not ctx.sync:
@@ -678,6 +760,7 @@ class _MixtureHead(torch.autograd.Function):
         base = base.contiguous()
         logw = logw.contiguous()
         nll = torch.empty(B, N, device=dev)
+        stack.nonfinite_counter(dev)
         nat.check(lib.gwtf_nll_from_state(ctypes.byref(stack.desc), nat.ptr(z), nat.ptr(ld), nat.ptr(base),
                                           nat.ptr(logw), B, N, nat.ptr(nll), None, _stream_ptr()),
                   'gwtf_nll_from_state')
@@ -723,15 +806,14 @@ def mixture_nll(stack, p, g, mu_base, lv_base, logits, training, want_nll=True):
     return z, ssum, nll
 
 
-def mixture_cdf(logits_row):
-    """Inclusive CDF of softmax(logits) the way np.random.choice builds it (flow_mixture.py:149-153):
-    fp32 probabilities, float64 cumsum, normalised; stored fp32 with the last entry pinned to 1."""
-    e = np.exp(logits_row.astype(np.float32))
-    probs = e / e.sum()
-    cdf = np.cumsum(probs.astype(np.float64))
-    cdf /= cdf[-1]
-    cdf = cdf.astype(np.float32)
-    cdf[-1] = np.float32(1.0)
+def mixture_cdf(logits):
+    """(B,K) logits on the device -> (B,K) inclusive CDF of softmax(logits) the way np.random.choice builds it
+    (flow_mixture.py:149-153): fp32 probabilities, float64 cumsum, normalised; stored fp32 with the last entry
+    pinned to 1.  Computed by a kernel (no host round trip; the reference syncs to numpy here, :149)."""
+    logits = logits.detach().float().contiguous()
+    cdf = torch.empty_like(logits)
+    nat.check(nat.lib().gwtf_mixture_cdf(nat.ptr(logits), logits.shape[0], logits.shape[1], nat.ptr(cdf), _stream_ptr()),
+              'gwtf_mixture_cdf')
     return cdf
 
 
@@ -739,7 +821,8 @@ def mixture_cdf(logits_row):
 def sample_mixture(stack, g, mu_base, lv_base, logits, n_points, seed, stream_id=0, idx=None, eps=None,
                    want_z=False):
     """Eval-mode sampling of n_points per shape -> samples (B,3,N), labels (B,N) int32 in 1..K,
-    z (B,3,N) or None.  `idx` (B,N) int32 / `eps` (B,3,N) replace the in-kernel Philox draws."""
+    z (B,3,N) or None.  `idx` (B,N) int32 / `eps` (B,3,N) replace the in-kernel Philox draws.
+    Nothing is read back to the host: the call only enqueues kernels on the current stream."""
     lib = nat.lib()
     if not g.is_cuda:
         raise nat.GwtfError('the flow stack runs on CUDA tensors only (got %s)' % g.device)
@@ -750,8 +833,7 @@ def sample_mixture(stack, g, mu_base, lv_base, logits, n_points, seed, stream_id
     params = stack.pack_params()
     bnbuf = stack.pack_bn()
     base = torch.stack([mu_base, lv_base], dim=1).contiguous()
-    host_logits = logits.detach().float().cpu().numpy()                             # as the reference: :149
-    cdf = torch.from_numpy(np.stack([mixture_cdf(r) for r in host_logits])).to(dev)
+    cdf = mixture_cdf(logits)
     samples = torch.empty(B, 3, n_points, device=dev)
     labels = torch.empty(B, n_points, device=dev, dtype=torch.int32)
     z = torch.empty(B, 3, n_points, device=dev) if want_z else None
@@ -759,42 +841,59 @@ def sample_mixture(stack, g, mu_base, lv_base, logits, n_points, seed, stream_id
         idx = idx.to(device=dev, dtype=torch.int32).contiguous()
     if eps is not None:
         eps = eps.to(device=dev, dtype=torch.float32).contiguous()
-    if lib.gwtf_engine() != 0:
-        # tensor-core engines: regroup the points by component and run the per-layer kernels in direct mode
-        # (needs the largest per-(shape, component) count on the host: one 4-byte read back)
-        K = stack.K
-        counts = torch.empty(B, K, device=dev, dtype=torch.int32)
-        nmax = torch.zeros(1, device=dev, dtype=torch.int32)
-        seed64, sid = ctypes.c_uint64(seed & (2 ** 64 - 1)), ctypes.c_uint32(stream_id & 0xFFFFFFFF)
-        nat.check(lib.gwtf_sample_plan(ctypes.byref(stack.desc), nat.ptr(cdf), B, n_points, seed64, sid, nat.ptr(idx),
-                                       nat.ptr(counts), nat.ptr(nmax), _stream_ptr()), 'gwtf_sample_plan')
-        nmax_pad = max(128, (int(nmax.item()) + 127) // 128 * 128)
-        if K * nmax_pad <= 3 * max(n_points, 128):      # very skewed mixtures: the fused kernel does less work
-            scratch = torch.empty(2 * K * B * 3 * nmax_pad, device=dev)
-            slot = torch.empty(B, n_points, device=dev, dtype=torch.int32)
-            nat.check(lib.gwtf_sample_layers(ctypes.byref(stack.desc), nat.ptr(params), nat.ptr(bnbuf), nat.ptr(film),
-                                             nat.ptr(base), nat.ptr(cdf), B, n_points, nmax_pad, seed64, sid,
-                                             nat.ptr(idx), nat.ptr(eps), nat.ptr(scratch), nat.ptr(slot),
-                                             nat.ptr(samples), nat.ptr(labels), nat.ptr(z), _stream_ptr()),
-                      'gwtf_sample_layers')
-            return samples, labels, z
-    nat.check(lib.gwtf_sample(ctypes.byref(stack.desc), nat.ptr(params), nat.ptr(bnbuf), nat.ptr(film), nat.ptr(base),
-                              nat.ptr(cdf), B, n_points, ctypes.c_uint64(seed & (2 ** 64 - 1)),
-                              ctypes.c_uint32(stream_id & 0xFFFFFFFF), nat.ptr(idx), nat.ptr(eps), nat.ptr(samples),
+    desc = ctypes.byref(stack.desc)
+    seed64, sid = ctypes.c_uint64(seed & (2 ** 64 - 1)), ctypes.c_uint32(stream_id & 0xFFFFFFFF)
+    if stack.fwd_engine() == nat.ENGINE_TC_FWD:
+        # tcgen05 forward: regroup the points by component inside each shape's row and run the per-layer kernels
+        # in direct mode; every buffer is sized from upper bounds, so there is no count read-back
+        need = int(lib.gwtf_sample_workspace_bytes(desc, B, n_points))
+        ws = stack._scratch('sample_ws', need, dev)
+        nat.check(lib.gwtf_sample_layers(desc, nat.ptr(params), nat.ptr(bnbuf), nat.ptr(film), nat.ptr(base),
+                                         nat.ptr(cdf), B, n_points, seed64, sid, nat.ptr(idx), nat.ptr(eps), nat.ptr(ws),
+                                         need, nat.ptr(samples), nat.ptr(labels), nat.ptr(z), _stream_ptr()),
+                  'gwtf_sample_layers')
+        return samples, labels, z
+    nat.check(lib.gwtf_sample(desc, nat.ptr(params), nat.ptr(bnbuf), nat.ptr(film), nat.ptr(base),
+                              nat.ptr(cdf), B, n_points, seed64, sid, nat.ptr(idx), nat.ptr(eps), nat.ptr(samples),
                               nat.ptr(labels), nat.ptr(z), _stream_ptr()), 'gwtf_sample')
     return samples, labels, z
 
 
-@torch.no_grad()
 def run_module_stack(stack, p, g, mode, training):
     """Per-module list API (flows.py:117,160; decoders.py:79) on a K=1 stack: every layer's
-    (p_out, mu, logvar), indexed by layer in DIRECT order.  Inference-only: the returned
-    tensors carry no autograd graph (training goes through Flow_Mixture_Model.decode)."""
+    (p_out, mu, logvar), indexed by layer in DIRECT order.
+
+    Gradients.  mode='inverse' with autograd enabled is differentiable in what the reference's losses consume
+    (losses.py:12-20,112-122): ps[0], the base-space sample, carries the graph, and so does the SUM of the
+    returned logvars (logvars[0] is returned as `S - sum(logvars[1:])` with S the differentiable per-dim
+    log-det sum of the kernels; the other entries are values only).  Per-layer intermediates (ps[1:], mus) are
+    values only.  mode='direct' is the sampling direction and never carries a graph; asking for it in training
+    mode with autograd enabled raises instead of silently dropping gradients."""
+    if mode not in ('direct', 'inverse'):
+        raise ValueError(mode)
+    if torch.is_grad_enabled():
+        if mode == 'direct' and training:
+            raise nat.GwtfError("mode='direct' (sampling) is not differentiable here: call it under torch.no_grad() "
+                                "or in eval mode; training goes through mode='inverse' / Flow_Mixture_Model.decode")
+        if mode == 'inverse':
+            z, ssum = stack.nll_pass(p.contiguous().float(), g, training)          # (1,B,3,N) each, with graph
+            ps, mus, lvs = _run_module_stack(stack, p, g, mode, training, update_stats=False)
+            ps = [z[0]] + ps[1:]
+            if len(lvs) > 1:
+                rest = torch.stack(lvs[1:]).sum(0)
+                lvs = [ssum[0] - rest] + lvs[1:]
+            else:
+                lvs = [ssum[0]]
+            return ps, mus, lvs
+    return _run_module_stack(stack, p, g, mode, training, update_stats=True)
+
+
+@torch.no_grad()
+def _run_module_stack(stack, p, g, mode, training, update_stats):
+    """The list API proper (values only)."""
     lib = nat.lib()
     if not p.is_cuda:
         raise nat.GwtfError('the flow stack runs on CUDA tensors only (got %s)' % p.device)
-    if mode not in ('direct', 'inverse'):
-        raise ValueError(mode)
     assert stack.K == 1
     L, Fd = stack.L, stack.F
     p = p.contiguous().float()
@@ -802,7 +901,7 @@ def run_module_stack(stack, p, g, mode, training):
     dev = p.device
     sync = training and _world() > 1
     stack.prepare()
-    film = stack.film(g, training, sync)
+    film = stack.film(g, training, sync, update_stats=update_stats)
     params = stack.pack_params()
     bnbuf = stack.pack_bn()
     desc = ctypes.byref(stack.desc)
@@ -838,7 +937,8 @@ def run_module_stack(stack, p, g, mode, training):
         bstat = torch.empty(L, 1, 2, 4, Fd, device=dev)
         nat.check(lib.gwtf_fwd_bstat(desc, nat.ptr(params), nat.ptr(mom), nat.ptr(sum1), n_total, nat.ptr(bstat), st),
                   'gwtf_fwd_bstat')
-        stack.update_point_bn(bstat, n_total)
+        if update_stats:
+            stack.update_point_bn(bstat, n_total)
     ps = [trio[l, 0] for l in range(L)]
     mus = [trio[l, 1] for l in range(L)]
     lvs = [trio[l, 2] for l in range(L)]

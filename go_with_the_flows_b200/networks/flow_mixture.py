@@ -29,7 +29,14 @@ class Flow_Mixture_Model(Local_Cond_RNVP_MC_Global_RNVP_VAE):
           list structure ('p_prior_samples'[0] = z_j, 'p_prior_logvars' summing to S_j) so any
           FlowMixtureNLL implementation can consume it.
       sample_seed (int | None): Philox seed of the sampling kernel; None draws one from torch's
-          global generator on every call (so torch.manual_seed governs it).
+          global generator on every call (so torch.manual_seed governs it).  With a fixed seed every
+          `decode` call still gets its own Philox stream: the per-model call counter `sample_calls` is
+          folded into the stream id, so the shape-by-shape evaluation loops of the reference
+          (training.py:355, evaluating.py:93, B = 1 per call) do not reuse one set of draws for every
+          shape; set `sample_calls = 0` to replay a sequence.
+      nonfinite_points(): how many per-point NLLs the kernels have written as NaN/inf since the last
+          call (device counter, one 4-byte read) -- the reference stops without an update on a NaN
+          loss (training.py:43-46); the loss itself is NaN in that case here too.
     """
 
     def __init__(self, **kwargs):
@@ -48,6 +55,7 @@ class Flow_Mixture_Model(Local_Cond_RNVP_MC_Global_RNVP_VAE):
         self.fused_nll = True
         self.sample_seed = None
         self.sample_stream = 0
+        self.sample_calls = 0
         self._stack = None
 
     # ------------------------------------------------------------------ sizing (flow_mixture.py:44-102)
@@ -100,6 +108,9 @@ class Flow_Mixture_Model(Local_Cond_RNVP_MC_Global_RNVP_VAE):
             self._stack = FlowStack([dec.coupling_layers() for dec in self.pc_decoder])
         return self._stack
 
+    def nonfinite_points(self):
+        return 0 if self._stack is None else self._stack.take_nonfinite()
+
     def _base(self, g_sample):
         """Base Gaussian; the reference re-evaluates p_prior once per component (models.py:171 via
         :163-166), which advances its BatchNorm running statistics K times per step -- kept."""
@@ -135,8 +146,9 @@ class Flow_Mixture_Model(Local_Cond_RNVP_MC_Global_RNVP_VAE):
         seed = self.sample_seed
         if seed is None:
             seed = int(torch.randint(0, 2 ** 62, (1,)).item())
-        samples, labels, _ = sample_mixture(stack, g_sample, mu_b, lv_b, logits, int(n_sampled_points), seed,
-                                            self.sample_stream)
+        stream = (self.sample_stream + 0x9E3779B9 * self.sample_calls) & 0xFFFFFFFF
+        self.sample_calls += 1
+        samples, labels, _ = sample_mixture(stack, g_sample, mu_b, lv_b, logits, int(n_sampled_points), seed, stream)
         if labeled_samples:
             return samples, labels.to(samples.dtype), logits
         out = []

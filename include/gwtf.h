@@ -48,35 +48,47 @@ extern "C" {
 #define GWTF_MAX_FEATURES 64
 #define GWTF_MOM_STRIDE 16
 
+/* Execution options ride in the descriptor the caller owns: the library keeps NO mutable process-global
+ * state (two stacks, or two streams, in one process never share anything) and is re-entrant per stream. */
+#define GWTF_ENGINE_DEFAULT (-1)  /* = GWTF_ENGINE_TC */
+#define GWTF_ENGINE_FMA 0         /* FP32 FMA pipe everywhere (reference engine for cross-checks) */
+#define GWTF_ENGINE_TC_FWD 2      /* tcgen05 persistent forward (3xTF32) + mma.sync register-fragment backward */
+#define GWTF_ENGINE_MMA 3         /* mma.sync m16n8k8 tf32 fragments, forward and backward (feature widths <= 64) */
+#define GWTF_ENGINE_TC 4          /* tcgen05 / TMEM forward AND backward (feature widths <= 39; wider -> MMA) */
+#define GWTF_FLAG_NO_PDL 1        /* launch the layer kernels without programmatic dependent launch */
+#define GWTF_PRECISION_3XTF32 0   /* fp32-grade: A*B ~ Ahi*Bhi + Alo*Bhi + Ahi*Blo */
+#define GWTF_PRECISION_TF32 1     /* single-pass TF32: eval-mode NLL without gradients and sampling only
+                                   * (per-point log-likelihood within 1e-5 of fp32, see tests/test_gpu_precision.py) */
+
+typedef struct gwtf_exchange gwtf_exchange;   /* opaque: peer-memory statistic exchange of one rank */
+
 typedef struct gwtf_stack_desc {
     int32_t n_components;                   /* K */
     int32_t n_layers;                       /* L = 3 * n_flows */
     int32_t n_features;                     /* F */
     int32_t rec_stride;                     /* floats per (component, layer) record in `params` */
     uint8_t warp_mask[GWTF_MAX_LAYERS];     /* bit d set: dim d is warped by layer l (flows.py:18-23) */
+    int32_t engine;                         /* GWTF_ENGINE_* */
+    int32_t flags;                          /* GWTF_FLAG_* */
+    int32_t eval_precision;                 /* GWTF_PRECISION_* of the no-grad eval NLL / sampling passes */
+    int32_t reserved;
+    gwtf_exchange* exchange;                /* rank exchange used by gwtf_*_all_ranks, or NULL */
+    int32_t* nonfinite;                     /* DEVICE counter, += number of non-finite per-point NLLs written by
+                                             * gwtf_nll_from_state / gwtf_fwd_all / gwtf_nll_fwd_eval* (the reference
+                                             * stops without an update on a NaN loss, training.py:43-46), or NULL */
 } gwtf_stack_desc;
 
 int gwtf_version(void);
-/* Contraction engine of the per-layer kernels:
- *   3 = warp-level tensor-core fragments (mma.sync m16n8k8 tf32, 3xTF32) for the forward AND backward
- *       layer phases, feature widths <= 64 (what engines 1-2 fall back to for widths > 39);
- *   2 = tcgen05 tensor cores for the forward phases, persistent warp-specialised kernel (3xTF32, TMEM
- *       accumulators, feature widths <= 39) + the mma.sync backward (default);
- *   1 = tcgen05 forward with one tile per 128-thread CTA + the mma.sync backward;
- *   0 = FP32 FMA pipe everywhere;  -1 = re-read the GWTF_TC environment variable.
- * Returns the previous setting (NOT an error code). */
-int gwtf_set_tensor_cores(int32_t enable);
-/* Programmatic dependent launch of the layer kernels (their parameter staging overlaps the predecessor's
- * tail): 1 = on (default), 0 = ordinary launches, -1 = re-read GWTF_PDL.  Returns the previous setting. */
-int gwtf_set_pdl(int32_t enable);
-/* The engine currently selected (0..3, environment resolved). */
-int gwtf_engine(void);
+/* The engine a descriptor resolves to for the forward (which=0) / backward (which=1) layer kernels. */
+int gwtf_resolved_engine(const gwtf_stack_desc* desc, int32_t which);
 /* Size in floats of the optional kept-activation buffer (`ybuf` of gwtf_fwd_layer / gwtf_fwd_all /
- * gwtf_bwd_layer / gwtf_bwd_all) for B clouds of N points under the CURRENT engine; the layout is private
- * to the engine, so the forward and backward calls that share a buffer must run under the same setting.
- * The tensor-core engines keep the sd1 output (engine 3: before, engines 1-2: after sd1_bn + FiLM, flows.py:100-104)
- * in MMA-fragment order: L*K*2*B*ceil(N/256)*256*roundup8(F) floats. */
+ * gwtf_bwd_layer / gwtf_bwd_all) for B clouds of N points under the descriptor's engine; the layout is private
+ * to the engine.  0 for the tcgen05 backward, which always recomputes.
+ * mma.sync backward: L*K*2*B*ceil(N/256)*256*roundup8(F) floats in MMA-fragment order. */
 int64_t gwtf_keep_floats(const gwtf_stack_desc* desc, int32_t B, int32_t N);
+/* Workspace queries of the single-call drivers (bytes; the caller allocates, the library never does). */
+int64_t gwtf_eval_layers_workspace_bytes(const gwtf_stack_desc* desc, int32_t B, int32_t N);
+int64_t gwtf_sample_workspace_bytes(const gwtf_stack_desc* desc, int32_t B, int32_t N);
 const char* gwtf_last_error_string(void);
 
 /* Record geometry shared with the Python packer.  offsets[0..5] = W0,bn0.weight,bn0.bias,W1,W2,b2
@@ -109,11 +121,13 @@ int gwtf_nll_fwd_eval(const gwtf_stack_desc* desc, const float* params, const fl
  *                    phase 1 is needed.  n_total = number of points the statistics are over
  *                    (B*N summed over ranks) -- the caller all-reduces mom/sum1 between phases.
  * gwtf_fwd_all     : single-process driver: moments + all layers + bstat + nll. */
-/* Eval-mode NLL (same result as gwtf_nll_fwd_eval) through the per-layer tensor-core kernels of the current
- * engine: scratch = 2*K*B*3*N floats, ld = K*B*N floats (both overwritten). */
+/* Eval-mode NLL (same result as gwtf_nll_fwd_eval) through the per-layer tensor-core kernels of the descriptor's
+ * engine; workspace of gwtf_eval_layers_workspace_bytes (overwritten).  desc->eval_precision selects fp32-grade
+ * 3xTF32 or single-pass TF32 contractions. */
 int gwtf_nll_fwd_eval_layers(const gwtf_stack_desc* desc, const float* params, const float* bnbuf,
                              const float* film, const float* points, const float* base, const float* logw,
-                             float* scratch, float* ld, int32_t B, int32_t N, float* nll, float* logp, void* stream);
+                             void* workspace, int64_t workspace_bytes, int32_t B, int32_t N, float* nll, float* logp,
+                             void* stream);
 int gwtf_fwd_moments(const gwtf_stack_desc* desc, const float* points, int32_t B, int32_t N,
                      double* mom, void* stream);
 int gwtf_fwd_layer(const gwtf_stack_desc* desc, int32_t layer, int32_t phase, int32_t train,
@@ -174,15 +188,25 @@ int gwtf_bwd_all(const gwtf_stack_desc* desc, int32_t train, const float* params
  * reference's DistributedDataParallel training (train_ae.py:77-78, torch.nn.SyncBatchNorm.convert_sync_batchnorm)
  * The statistic sums of every layer phase are exchanged through NVLink peer memory by a push / flag /
  * add kernel (csrc/gwtf_exchange.cuh) instead of a collective call per phase.
- * gwtf_exchange_attach : recv[r] / flags[r] = device pointers, valid on THIS device, to rank r's receive
+ * gwtf_exchange_create : recv[r] / flags[r] = device pointers, valid on THIS device, to rank r's receive
  *                        buffer (2*world*slot_doubles doubles) and flag array (world uint64, zeroed before the
  *                        first exchange and never written by the host afterwards); symmetric / IPC memory.
- *                        world = 1 detaches.  All ranks must issue the same sequence of exchanges.
+ *                        timeout_s: seconds a rank waits for its peers before the exchange kernel gives up with
+ *                        a (sticky) launch failure instead of hanging (<= 0: 600 s, NCCL-like).  All ranks must issue the same
+ *                        sequence of exchanges; the handle owns the sequence counter, so one handle serves
+ *                        one stream of work at a time (create one per concurrent stream).
  * gwtf_exchange_sum    : in-place sum over ranks of n <= slot_doubles doubles (stream ordered).
- * gwtf_fwd_all_ranks / gwtf_bwd_all_ranks : the single-call drivers with n_total = points on all ranks. */
-int gwtf_exchange_attach(int32_t rank, int32_t world, void* const* recv, void* const* flags, int32_t slot_doubles);
-int gwtf_exchange_world(void);
-int gwtf_exchange_sum(double* data, int32_t n, void* stream);
+ * gwtf_exchange_resync : after a failed call on one rank: every rank calls it (collectively, after a barrier
+ *                        of the caller's) to realign the sequence counters to `seq`.
+ * gwtf_fwd_all_ranks / gwtf_bwd_all_ranks : the single-call drivers with n_total = points on all ranks;
+ *                        they use desc->exchange. */
+int gwtf_exchange_create(int32_t rank, int32_t world, void* const* recv, void* const* flags, int32_t slot_doubles,
+                         double timeout_s, gwtf_exchange** out);
+int gwtf_exchange_destroy(gwtf_exchange* x);
+int gwtf_exchange_world(const gwtf_exchange* x);
+uint64_t gwtf_exchange_seq(const gwtf_exchange* x);
+int gwtf_exchange_resync(gwtf_exchange* x, uint64_t seq);
+int gwtf_exchange_sum(gwtf_exchange* x, double* data, int32_t n, void* stream);
 int gwtf_fwd_all_ranks(const gwtf_stack_desc* desc, int32_t train, const float* params, const float* bnbuf,
                        const float* film, const float* points, const float* base, const float* logw,
                        float* ubuf, float* ld, float* ssum, float* ybuf, double* mom, double* sum1, float* bstat,
@@ -204,16 +228,24 @@ int gwtf_sample(const gwtf_stack_desc* desc, const float* params, const float* b
                 const float* film, const float* base, const float* cdf, int32_t B, int32_t N,
                 uint64_t seed, uint32_t stream_id, const int32_t* idx_in, const float* eps_in,
                 float* samples, int32_t* labels, float* z_out, void* stream);
-/* The same sampling pass through the per-layer tensor-core kernels of the current engine: points regrouped by the
- * component they drew.  gwtf_sample_plan counts the draws (counts (B,K) int32, *nmax = largest count; device
- * memory); the caller reads *nmax back, rounds it up to a multiple of 128 (nmax_pad) and provides
- * scratch = 2*K*B*3*nmax_pad floats and slot = B*N int32.  Results equal gwtf_sample's (same Philox streams). */
-int gwtf_sample_plan(const gwtf_stack_desc* desc, const float* cdf, int32_t B, int32_t N, uint64_t seed,
-                     uint32_t stream_id, const int32_t* idx_in, int32_t* counts, int32_t* nmax, void* stream);
+/* cdf (B,K) <- inclusive CDF of softmax(logits (B,K)) the way np.random.choice builds it (flow_mixture.py:149-153):
+ * fp32 probabilities (e = fp32(exp(fp64(logit)))), float64 cumsum, normalised, last entry pinned to 1.  On the
+ * device, so the sampling call never reads anything back to the host. */
+int gwtf_mixture_cdf(const float* logits, int32_t B, int32_t K, float* cdf, void* stream);
+/* The same sampling pass through the per-layer tcgen05 kernels: the points of every shape are regrouped by the
+ * component they drew (segments inside the shape's row, sized from upper bounds -- no host read-back), pushed
+ * through the L direct layers, gathered back.  Results equal gwtf_sample's (same Philox streams, bit-exact labels).
+ * workspace: gwtf_sample_workspace_bytes.  Needs the tcgen05 forward (feature widths <= 39). */
 int gwtf_sample_layers(const gwtf_stack_desc* desc, const float* params, const float* bnbuf, const float* film,
-                       const float* base, const float* cdf, int32_t B, int32_t N, int32_t nmax_pad, uint64_t seed,
-                       uint32_t stream_id, const int32_t* idx_in, const float* eps_in, float* scratch, int32_t* slot,
+                       const float* base, const float* cdf, int32_t B, int32_t N, uint64_t seed, uint32_t stream_id,
+                       const int32_t* idx_in, const float* eps_in, void* workspace, int64_t workspace_bytes,
                        float* samples, int32_t* labels, float* z_out, void* stream);
+
+/* ---- optimizer (lib/networks/optimizers.py:42-74): one fused AMSGrad / Adam step over a flat fp32 buffer.
+ * exp_avg, exp_avg_sq (and max_exp_avg_sq, NULL = no AMSGrad) are updated in place; `step` counts from 1 (bias
+ * corrections 1-beta1^step, sqrt(1-beta2^step)); weight_decay is added to the update un-scaled by lr (:69-72). */
+int gwtf_adam_step(float* p, const float* g, float* exp_avg, float* exp_avg_sq, float* max_exp_avg_sq, int64_t n,
+                   double lr, double beta1, double beta2, double eps, double weight_decay, int64_t step, void* stream);
 
 #ifdef __cplusplus
 }

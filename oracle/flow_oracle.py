@@ -367,9 +367,17 @@ def box_muller(w: np.ndarray) -> np.ndarray:
 
 def mixture_cdf(logits_row: np.ndarray) -> np.ndarray:
     """flow_mixture.py:149-150 probs, then the float64 inclusive cumsum numpy's
-    `choice` builds; stored as float32 with the last entry forced to 1."""
-    e = np.exp(logits_row.astype(np.float32))
-    probs = e / e.sum()
+    `choice` builds; stored as float32 with the last entry forced to 1.
+
+    The fp32 exponential is taken as the correctly rounded one, fp32(exp(fp64(x))), and the fp32 sum runs left to
+    right: numpy's own float32 `exp` may differ from it in the last bit depending on the SIMD path it takes, and
+    a rule that both this restatement and the CUDA kernel (k_mixture_cdf) can reproduce bit for bit is what makes
+    the component assignment bit-exact.  A one-ulp change of a probability moves a cdf boundary by ~6e-8."""
+    e = np.exp(logits_row.astype(np.float32).astype(np.float64)).astype(np.float32)
+    tot = np.float32(0.0)
+    for v in e:
+        tot = np.float32(tot + v)
+    probs = e / tot
     cdf = np.cumsum(probs.astype(np.float64))
     cdf /= cdf[-1]
     cdf = cdf.astype(np.float32)

@@ -52,6 +52,11 @@ CASES = {
     'small_mid_global': (dict(n_components=3, params_reduce_mode='none', weights_type='global_weights',
                               p_decoder_n_flows=1, p_decoder_n_features=27, g_latent_space_size=8,
                               p_decoder_base_type='freevar'), 3, 37),
+    # the feature width of config_autoencoding.yaml / config_SVR.yaml (F = 33: FP = 36 on the FMA engine, 40 on the
+    # tensor-core engines), freevar base, learned weights, ragged N spanning two 128-point tiles
+    'small_c3_freevar': (dict(n_components=3, params_reduce_mode='none', weights_type='learned_weights',
+                              p_decoder_n_flows=1, p_decoder_n_features=33, g_latent_space_size=16,
+                              p_decoder_base_type='freevar', p_decoder_base_var=-3.596), 3, 150),
 }
 
 

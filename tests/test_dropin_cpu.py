@@ -43,7 +43,7 @@ def test_cabi_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(handle, name), name
     assert set(_native.EXPORTED) == declared
-    assert _native.lib().gwtf_version() == 1
+    assert _native.lib().gwtf_version() == 2
 
 
 def test_flow_modules_refuse_cpu_tensors():
@@ -116,29 +116,43 @@ def test_flat_storage_survives_syncbn_conversion_and_zero_grad():
 
 
 def test_cabi_host_side_queries_without_a_gpu():
-    """Entry points that only do host arithmetic / argument checks: engine selection, kept-activation
-    buffer size, exchange attachment validation (no kernel is launched)."""
+    """Entry points that only do host arithmetic / argument checks: engine resolution, kept-activation
+    buffer and workspace sizes, exchange handle validation (no kernel is launched)."""
     import ctypes
     from go_with_the_flows_b200 import _native as nat
     lib = nat.lib()
-    prev = lib.gwtf_set_tensor_cores(2)
-    try:
-        assert lib.gwtf_engine() == 2
-        desc = nat.StackDesc()
-        desc.n_components, desc.n_layers, desc.n_features = 4, 33, 37
-        desc.rec_stride = lib.gwtf_rec_stride(37)
-        for l in range(33):
-            desc.warp_mask[l] = 1 << (l % 3)
-        # L * K * 2 nets * B * roundup256(N) * roundup8(F) floats under the tensor-core engines
-        assert lib.gwtf_keep_floats(ctypes.byref(desc), 64, 2048) == 33 * 4 * 2 * 64 * 2048 * 40
-        assert lib.gwtf_keep_floats(ctypes.byref(desc), 3, 50) == 33 * 4 * 2 * 3 * 256 * 40
-        lib.gwtf_set_tensor_cores(0)          # FMA engine: (L,K,2,F,B,N)
-        assert lib.gwtf_keep_floats(ctypes.byref(desc), 3, 50) == 33 * 4 * 2 * 37 * 3 * 50
-    finally:
-        lib.gwtf_set_tensor_cores(prev)
-    assert lib.gwtf_exchange_world() == 1
-    assert lib.gwtf_exchange_attach(0, 1, None, None, 0) == 0             # single rank: detach / no-op
-    assert lib.gwtf_exchange_attach(0, 4, None, None, 0) != 0             # several ranks need peer buffers
-    assert lib.gwtf_exchange_attach(5, 4, None, None, 0) != 0
-    assert lib.gwtf_exchange_world() == 1
-    assert lib.gwtf_set_pdl(lib.gwtf_set_pdl(1)) in (0, 1)
+    desc = nat.StackDesc()
+    desc.n_components, desc.n_layers, desc.n_features = 4, 33, 37
+    desc.rec_stride = lib.gwtf_rec_stride(37)
+    for l in range(33):
+        desc.warp_mask[l] = 1 << (l % 3)
+    d = ctypes.byref(desc)
+    desc.engine = nat.ENGINE_TC_FWD
+    assert lib.gwtf_resolved_engine(d, 0) == nat.ENGINE_TC_FWD and lib.gwtf_resolved_engine(d, 1) == nat.ENGINE_MMA
+    # L * K * 2 nets * B * roundup256(N) * roundup8(F) floats under the mma.sync backward
+    assert lib.gwtf_keep_floats(d, 64, 2048) == 33 * 4 * 2 * 64 * 2048 * 40
+    assert lib.gwtf_keep_floats(d, 3, 50) == 33 * 4 * 2 * 3 * 256 * 40
+    desc.engine = nat.ENGINE_FMA                  # FMA engine: (L,K,2,F,B,N)
+    assert lib.gwtf_keep_floats(d, 3, 50) == 33 * 4 * 2 * 37 * 3 * 50
+    desc.engine = nat.ENGINE_DEFAULT              # tcgen05 forward and backward: the backward always recomputes
+    assert lib.gwtf_resolved_engine(d, 0) == nat.ENGINE_TC_FWD and lib.gwtf_resolved_engine(d, 1) == nat.ENGINE_TC
+    assert lib.gwtf_keep_floats(d, 3, 50) == 0
+    desc.n_features, desc.rec_stride = 44, lib.gwtf_rec_stride(44)      # wider than the tcgen05 tile: mma.sync
+    assert lib.gwtf_resolved_engine(d, 0) == nat.ENGINE_MMA and lib.gwtf_resolved_engine(d, 1) == nat.ENGINE_MMA
+    desc.n_features, desc.rec_stride = 37, lib.gwtf_rec_stride(37)
+    desc.engine = 1                               # the retired one-tile-per-CTA engine is not a valid choice
+    assert lib.gwtf_resolved_engine(d, 0) == -1
+    desc.engine = nat.ENGINE_DEFAULT
+    assert lib.gwtf_eval_layers_workspace_bytes(d, 4, 2048) == 4 * (2 * 4 * 4 * 3 * 2048 + 4 * 4 * 2048)
+    npad = 2560 + 128 * 4                          # roundup128(2500) + 128 K
+    assert lib.gwtf_sample_workspace_bytes(d, 2, 2500) >= 4 * (2 * 2 * 3 * npad + 2 * 2500)
+    out = ctypes.c_void_p()
+    assert lib.gwtf_exchange_world(None) == 1
+    assert lib.gwtf_exchange_create(0, 1, None, None, 0, 0.0, ctypes.byref(out)) == 0   # single rank: no peers needed
+    assert lib.gwtf_exchange_world(out) == 1 and lib.gwtf_exchange_seq(out) == 0
+    assert lib.gwtf_exchange_resync(out, 5) == 0 and lib.gwtf_exchange_seq(out) == 5
+    assert lib.gwtf_exchange_resync(out, 3) != 0                                         # never backwards
+    assert lib.gwtf_exchange_destroy(out) == 0
+    assert lib.gwtf_exchange_create(0, 4, None, None, 0, 0.0, ctypes.byref(out)) != 0   # several ranks need peer buffers
+    assert lib.gwtf_exchange_create(5, 4, None, None, 0, 0.0, ctypes.byref(out)) != 0
+    assert b'rank' in lib.gwtf_last_error_string()

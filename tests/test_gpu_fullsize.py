@@ -9,13 +9,16 @@ from tests.util import max_rel, nll_err, rel_l2
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=['mma', 'tcgen05_persistent', 'tcgen05', 'fma'], autouse=True)
+@pytest.fixture(params=['tcgen05', 'tcgen05_fwd', 'mma', 'fma'], autouse=True)
 def contraction_engine(request):
-    from go_with_the_flows_b200 import _native
-    lib = _native.lib()
-    prev = lib.gwtf_set_tensor_cores({'mma': 3, 'tcgen05_persistent': 2, 'tcgen05': 1, 'fma': 0}[request.param])
+    """Every GPU parity test runs on every engine of the per-layer kernels: tcgen05 forward + backward (default),
+    tcgen05 forward + mma.sync backward, mma.sync fragments, and the FP32 FMA pipe."""
+    from go_with_the_flows_b200 import _native as nat
+    from go_with_the_flows_b200 import flowstack
+    prev = flowstack.set_default('engine', {'tcgen05': nat.ENGINE_TC, 'tcgen05_fwd': nat.ENGINE_TC_FWD,
+                                            'mma': nat.ENGINE_MMA, 'fma': nat.ENGINE_FMA}[request.param])
     yield request.param
-    lib.gwtf_set_tensor_cores(prev)
+    flowstack.set_default('engine', prev)
 
 
 def _model(cfg_name='generative'):
@@ -47,6 +50,23 @@ def _oracle(sd, cfg, p, g, training, dtype):
     return out, p.grad, g.grad, sd
 
 
+_ORACLE_CACHE = {}
+
+
+def oracle_case(cfg_name, B, N, training):
+    """fp64 + fp32 CPU-oracle results of a full-size case (seeded model, synthetic inputs), computed once per session
+    and shared by the engine parametrisation."""
+    key = (cfg_name, B, N, training)
+    if key not in _ORACLE_CACHE:
+        cfg, model = _model(cfg_name)
+        sd0 = {k: v.clone() for k, v in model.state_dict().items()}
+        p, g = _inputs(B, N, cfg['g_latent_space_size'])
+        r64 = _oracle(sd0, cfg, p, g, training, torch.float64)
+        r32 = _oracle(sd0, cfg, p, g, training, torch.float32)
+        _ORACLE_CACHE[key] = (cfg, p, g, r64, r32)
+    return _ORACLE_CACHE[key]
+
+
 def _grad_err(named, sd, key_filter):
     num = den = 0.0
     for k, v in sd.items():
@@ -62,11 +82,8 @@ def _grad_err(named, sd, key_filter):
 @pytest.mark.parametrize('training', [False, True])
 def test_c1_airplane_4x2048_against_fp64_oracle(training):
     from go_with_the_flows_b200.networks.losses import FlowMixtureNLL
-    cfg, model = _model()
-    sd0 = {k: v.clone() for k, v in model.state_dict().items()}
-    p, g = _inputs(4, 2048, cfg['g_latent_space_size'])
-    want, dp64, dg64, sd64 = _oracle(sd0, cfg, p, g, training, torch.float64)
-    w32, dp32, dg32, sd32 = _oracle(sd0, cfg, p, g, training, torch.float32)
+    cfg, p, g, (want, dp64, dg64, sd64), (w32, dp32, dg32, sd32) = oracle_case('generative', 4, 2048, training)
+    _, model = _model()
     model = model.cuda()
     model.mode = 'training'
     model.train(training)

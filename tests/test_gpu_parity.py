@@ -12,15 +12,16 @@ from tests.util import GOLDEN_CASES, Golden, build_dropin, max_rel
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=['mma', 'tcgen05_persistent', 'tcgen05', 'fma'], autouse=True)
+@pytest.fixture(params=['tcgen05', 'tcgen05_fwd', 'mma', 'fma'], autouse=True)
 def contraction_engine(request):
-    """Every GPU parity test runs on both engines of the per-layer kernels: tcgen05 tensor cores
-    (3xTF32, default) and the FP32 FMA pipe."""
-    from go_with_the_flows_b200 import _native
-    lib = _native.lib()
-    prev = lib.gwtf_set_tensor_cores({'mma': 3, 'tcgen05_persistent': 2, 'tcgen05': 1, 'fma': 0}[request.param])
+    """Every GPU parity test runs on every engine of the per-layer kernels: tcgen05 forward + backward (default),
+    tcgen05 forward + mma.sync backward, mma.sync fragments, and the FP32 FMA pipe."""
+    from go_with_the_flows_b200 import _native as nat
+    from go_with_the_flows_b200 import flowstack
+    prev = flowstack.set_default('engine', {'tcgen05': nat.ENGINE_TC, 'tcgen05_fwd': nat.ENGINE_TC_FWD,
+                                            'mma': nat.ENGINE_MMA, 'fma': nat.ENGINE_FMA}[request.param])
     yield request.param
-    lib.gwtf_set_tensor_cores(prev)
+    flowstack.set_default('engine', prev)
 
 NLL_TOL = 1e-4        # north star: per-point log-likelihood within 1e-4 relative (fp32 path)
 GRAD_TOL = 1e-4       # norm-wise on gradients

@@ -7,7 +7,7 @@ import torch
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
 GOLDEN_CASES = ['small_free_learned', 'small_freevar_global', 'small_fixed_learned', 'small_wide_learned',
-                'small_mid_global']
+                'small_mid_global', 'small_c3_freevar']
 
 
 class Golden:
