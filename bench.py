@@ -1,21 +1,28 @@
 #!/usr/bin/env python
-"""Benchmark of the mixture-of-flows hot path (BASELINE.json metric: points/sec fwd+bwd mixture NLL).
+"""Benchmark of the mixture-of-flows hot path (BASELINE.json metric: points/sec fwd+bwd mixture NLL and sampling).
 
     python bench.py --gpus N --steps K --warmup W            # our CUDA path (torchrun for N > 1)
-    python bench.py --impl reference --steps K --warmup W     # the reference algorithm on host cores
+    python bench.py --impl reference --steps K --warmup W     # the reference's own modules on the host cores
 
-A step = one train-mode (batch-statistics BatchNorm) forward + backward of the K-component
-mixture-of-flows NLL over one synthetic batch: `Flow_Mixture_Model.decode` + `FlowMixtureNLL` +
-`.backward()`, i.e. everything between the shape latent / point cloud and the gradients of every
-decoder parameter, the latent, the base Gaussian and the mixture weights.  Workload = BASELINE.json
-configs[1]: config_generative_modeling_airplane.yaml model (K=4, 33 coupling layers, F=37, G=128),
-64 clouds x 2048 points per GPU, random init (seed 0), synthetic clouds N(0, 0.2^2), latents N(0, 0.5^2).
+Headline (`value`, `e2e`): a step = one train-mode (batch-statistics BatchNorm) forward + backward of the
+K-component mixture-of-flows NLL over one synthetic batch: `Flow_Mixture_Model.decode` + `FlowMixtureNLL` +
+`.backward()`, i.e. everything between the shape latent / point cloud and the gradients of every decoder
+parameter, the latent, the base Gaussian and the mixture weights.  Workload = BASELINE.json configs[1] (C2):
+config_generative_modeling_airplane.yaml model (K=4, 33 coupling layers, F=37, G=128), 64 clouds x 2048 points
+per GPU (weak scaling), random init (seed 0), synthetic clouds N(0, 0.2^2), latents N(0, 0.5^2).
 
-Prints ONE JSON line (rank 0).  `value` times the step with inputs resident in HBM; `e2e` times the
-same step through the public module API from pinned host buffers (H2D of points + latents, D2H of
-the loss inside the timed region).  `roofline` compares the step's own kernels (CUDA-event timed, no
-Python in between) with the FP32 FMA pipe, which is what binds this path (~49 kFLOP
-per byte); the FMA peak is measured live by an FFMA probe kernel on the same GPU.
+`extra` holds the other BASELINE configs, each run on EVERY rank (shapes sharded, no collective unless it is a
+train step) with the aggregate over ranks and its own roofline:
+  eval_nll      C1-shaped eval-mode NLL (fp32-grade and the single-pass TF32 tier)
+  c3_step       config_autoencoding.yaml (F=33, G=512, freevar) train step
+  strong        C2 at the reference's semantics: 64 clouds in total, 64/N per GPU (train_ae.py:77-78)
+  sampling_c4   config_SVR.yaml decoder: 256 latents x 2048 points and 64 x 2500
+  sampling_c5   sweep 2k / 16k / 128k / 1M points x 256 latents, airplane decoder
+
+Roofline accounting: algorithmic contraction FLOPs over CUDA-event time.
+Tensor kernels are rated against MEASURED_PEAKS.json `bf16_tflops` / 2 (dense TF32 runs at half the bf16 rate) / 3
+(fp32-grade 3xTF32 issues three MMAs per product) -- "of measured"; `frac_of_fma_peak` rates the same number
+against the FP32 FMA pipe (live FFMA probe), which is what the >= 50 % target of the north star is quoted on.
 """
 import argparse
 import ctypes
@@ -38,6 +45,16 @@ def flops_per_point(F, K, L):
     (F*k + F*F + F*w) MAC = 4(F^2+3F) FLOP forward; backward (dgrad + wgrad) = 2x forward."""
     fwd = K * L * 4 * (F * F + 3 * F)
     return fwd, 3 * fwd
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        with open(path) as fh:
+            d = json.load(fh)
+        return {'bf16_tflops': float(d['bf16_tflops']), 'bf16_tflops_sustained': float(d.get('bf16_tflops_sustained', d['bf16_tflops'])),
+                'hbm_gbs': float(d['hbm_gbs']), 'source': 'measured'}
+    return {'bf16_tflops': 1590.0, 'bf16_tflops_sustained': 1400.0, 'hbm_gbs': 6650.0, 'source': 'fallback'}
 
 
 def build_model(cfg_name, device):
@@ -103,28 +120,66 @@ class ClockSampler:
                 'reasons': sorted(reasons), 'samples': len(sm)}
 
 
-def oracle_step_time(cfg_name, B, N, steps, warmup):
-    """The reference algorithm (CPU restatement in oracle/, same ATen ops as lib/networks) timed on
-    the host cores: train-mode forward + backward of the mixture NLL on a bounded sample."""
-    from oracle import flow_oracle as fo
+# ---------------------------------------------------------------------------------------------
+# CPU arms: the reference's own modules (staged by build() into oracle/_ref, git-ignored) or the oracle port
+# ---------------------------------------------------------------------------------------------
+def _reference_modules():
+    ref_root = os.path.join(ROOT, 'oracle', '_ref')
+    if not os.path.isdir(os.path.join(ref_root, 'lib', 'networks')):
+        return None
+    sys.dont_write_bytecode = True
+    if ref_root not in sys.path:
+        sys.path.insert(0, ref_root)
+    try:
+        from lib.networks.flow_mixture import Flow_Mixture_Model as RefModel
+        from lib.networks.losses import FlowMixtureNLL as RefNLL
+        return RefModel, RefNLL
+    except Exception:
+        return None
+
+
+def cpu_step_time(cfg_name, B, N, steps, warmup):
+    """Train-mode forward + backward of the mixture NLL on the host cores, bounded sample of the workload.
+    -> (seconds per step, threads, kind)."""
     torch.set_num_threads(os.cpu_count() or 1)
-    cfg, model = build_model(cfg_name, 'cpu')
-    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
-    for k, v in sd.items():
-        if v.is_floating_point() and k.startswith(('pc_decoder', 'p_prior', 'mixture_weights')) \
-                and 'running' not in k and not k.endswith('eps'):
-            v.requires_grad_(True)
+    from go_with_the_flows_b200 import configs
+    cfg = dict(configs.BY_NAME[cfg_name])
     p, g = synthetic(B, N, cfg['g_latent_space_size'])
-    g.requires_grad_(True)
+    ref = _reference_modules()
+    if ref is not None:
+        RefModel, RefNLL = ref
+        torch.manual_seed(0)
+        model = RefModel(**cfg)
+        model.mode = 'training'
+        model.train()
+        loss_fn = RefNLL()
+        g.requires_grad_(True)
 
-    def step():
-        for v in sd.values():
-            v.grad = None
-        out = fo.mixture_nll(p, g, sd, base_type=cfg['p_decoder_base_type'], weights_type=cfg['weights_type'],
-                             training=True, base_var=cfg['p_decoder_base_var'])
-        out['pnll'].backward()
-        return float(out['pnll'])
+        def step():
+            model.zero_grad()
+            out, logits = model.decode(p, g, N, False, False)
+            loss = loss_fn(out, logits)
+            loss.backward()
+            return float(loss)
+        kind = 'reference'
+    else:
+        from oracle import flow_oracle as fo
+        _, model = build_model(cfg_name, 'cpu')
+        sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+        for k, v in sd.items():
+            if v.is_floating_point() and k.startswith(('pc_decoder', 'p_prior', 'mixture_weights')) \
+                    and 'running' not in k and not k.endswith('eps'):
+                v.requires_grad_(True)
+        g.requires_grad_(True)
 
+        def step():
+            for v in sd.values():
+                v.grad = None
+            out = fo.mixture_nll(p, g, sd, base_type=cfg['p_decoder_base_type'], weights_type=cfg['weights_type'],
+                                 training=True, base_var=cfg['p_decoder_base_var'])
+            out['pnll'].backward()
+            return float(out['pnll'])
+        kind = 'port'
     for _ in range(warmup):
         step()
     times = []
@@ -132,7 +187,14 @@ def oracle_step_time(cfg_name, B, N, steps, warmup):
         t0 = time.perf_counter()
         step()
         times.append(time.perf_counter() - t0)
-    return sum(times) / len(times), torch.get_num_threads()
+    return sum(times) / len(times), torch.get_num_threads(), kind
+
+
+def workload_name(args):
+    if args.config == 'generative':
+        return 'C2: config_generative_modeling_airplane model (K=4,L=33,F=37,G=128), train-mode fwd+bwd mixture NLL, ' \
+               '%d clouds x %d points per GPU' % (args.batch, args.points)
+    return '%s config, train-mode fwd+bwd mixture NLL, %d clouds x %d points per GPU' % (args.config, args.batch, args.points)
 
 
 def run_reference(args):
@@ -142,32 +204,89 @@ def run_reference(args):
     B, N = 4, args.points
     steps = max(1, min(args.steps, 3))
     warmup = max(1, min(args.warmup, 1))
-    sec, cores = oracle_step_time(args.config, B, N, steps, warmup)
+    sec, cores, kind = cpu_step_time(args.config, B, N, steps, warmup)
     value = B * N / sec
-    sample = 'train-mode fwd+bwd mixture NLL, %d clouds x %d points per step (autograd holds ~1 GB/shape), ' \
-             '%d timed steps after %d warm-up' % (B, N, steps, warmup)
+    sample = 'train-mode fwd+bwd mixture NLL, %d clouds x %d points per step (autograd holds ~1 GB/shape; B=4 is the ' \
+             'CPU path\'s best per-point operating point), %d timed steps after %d warm-up' % (B, N, steps, warmup)
     line = {
         'impl': 'reference', 'metric': 'points/sec fwd+bwd mixture-flow NLL', 'value': value, 'unit': 'points/s',
         'n_gpus': args.gpus, 'steps': steps, 'warmup': warmup, 'ms_per_step': sec * 1e3, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
         'config': {'workload': workload_name(args), 'cpu_sample_clouds': B},
-        'cpu_baseline': {'value': value, 'unit': 'points/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+        'cpu_baseline': {'value': value, 'unit': 'points/s', 'cores': cores, 'kind': kind, 'sample': sample},
         'e2e': {'value': value, 'unit': 'points/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     }
     print(json.dumps(line), flush=True)
 
 
-def workload_name(args):
-    return 'C2: config_generative_modeling_airplane model (K=4,L=33,F=37,G=128), train-mode fwd+bwd mixture NLL, ' \
-           '%d clouds x %d points per GPU' % (args.batch, args.points) if args.config == 'generative' else \
-           '%s config, train-mode fwd+bwd mixture NLL, %d clouds x %d points per GPU' % (args.config, args.batch,
-                                                                                       args.points)
+# ---------------------------------------------------------------------------------------------
+# device-side timing helpers
+# ---------------------------------------------------------------------------------------------
+class Env:
+    def __init__(self, world, rank, dev):
+        self.world, self.rank, self.dev = world, rank, dev
+        self.flush_buf = torch.empty(256 * 1024 * 1024 // 4, device=dev)
+
+    def barrier(self):
+        if self.world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(self, ms):
+        t = torch.tensor([ms], device=self.dev, dtype=torch.float64)
+        if self.world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0])
+
+    def timed(self, fn, reps, warmup=1, flush=True):
+        """Mean CUDA-event time of `fn` over `reps` calls (L2 flushed before each), max over ranks."""
+        for _ in range(warmup):
+            fn()
+        self.barrier()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+        for e0, e1 in evs:
+            if flush:
+                self.flush_buf.fill_(0.0)
+            e0.record()
+            fn()
+            e1.record()
+        self.barrier()
+        return self.max_over_ranks(sum(e0.elapsed_time(e1) for e0, e1 in evs) / reps)
 
 
-def kernel_only_times(model, p, g, reps, keep=None):
+def make_step(model, world, N):
+    from go_with_the_flows_b200.networks.losses import FlowMixtureNLL
+    loss_fn = FlowMixtureNLL()
+    stack = model.flow_stack()
+    stack.prepare()
+    params_all = list(model.parameters())
+    owned = set()
+    for name in stack.grad_masters:          # decoder tensors: averaged across ranks inside backward
+        owned.update(id(q) for q in stack.masters[name].params)
+    params_other = [q for q in params_all if id(q) not in owned]
+
+    def step(p, g):
+        for q in params_all:
+            q.grad = None
+        g = g.detach().requires_grad_(True)
+        out_dec, logits = model.decode(p, g, N)
+        pnll = loss_fn(out_dec, logits)
+        pnll.backward()
+        if world > 1:
+            grads = [q.grad for q in params_other if q.grad is not None]
+            flat = torch._utils._flatten_dense_tensors(grads)
+            dist.all_reduce(flat)
+            flat.div_(world)
+            for gr, fl in zip(grads, torch._utils._unflatten_dense_tensors(flat, grads)):
+                gr.copy_(fl)
+        return pnll
+    return step
+
+
+def kernel_only_times(model, p, g, reps):
     """CUDA-event time of the step's own kernels with nothing in between: forward driver
     (moments + 2 phases x L layers + bstat + nll) and backward driver (seed + 2 phases x L + finish),
-    plus each phase class timed over the L layers."""
+    plus each phase class timed over the L layers (ordinary launches)."""
     from go_with_the_flows_b200 import _native as nat
     from go_with_the_flows_b200.flowstack import _stream_ptr
     lib = nat.lib()
@@ -199,12 +318,13 @@ def kernel_only_times(model, p, g, reps, keep=None):
     dbase = torch.zeros_like(base)
     dlogw = torch.zeros_like(logw)
     dpoints = torch.zeros_like(p)
-    desc = ctypes.byref(stack.desc)
+    desc_obj = nat.StackDesc.from_buffer_copy(stack.desc)
+    desc_obj.exchange = None
+    desc_obj.nonfinite = None
+    desc = ctypes.byref(desc_obj)
     P = nat.ptr
     n_total = float(B * N)
-    # kept activations follow the product default (FlowStack.keep_activations: on for the mma engine)
-    if keep is None:
-        keep = stack.keep_activations if stack.keep_activations is not None else lib.gwtf_engine() != 0
+    keep = bool(stack.keep_activations) and int(lib.gwtf_keep_floats(desc, B, N)) > 0
     ybuf = torch.empty(int(lib.gwtf_keep_floats(desc, B, N)), device=dev) if keep else None
 
     def fwd():
@@ -244,56 +364,143 @@ def kernel_only_times(model, p, g, reps, keep=None):
     out = {'fwd_ms': timed(fwd), 'bwd_ms': timed(bwd), 'kept': bool(keep), 'kept_bytes': 4 * ybuf.numel() if keep else 0}
     # one launch class at a time, ordinary launches: chaining a kernel behind ITSELF with programmatic dependent
     # launch (which the real sequence never does) makes the early CTAs of launch n+1 compete with launch n
-    prev_pdl = lib.gwtf_set_pdl(0)
+    desc_obj.flags |= nat.FLAG_NO_PDL
     for name, kind, phase in (('fwd_stats', 'fwd', 0), ('fwd_apply', 'fwd', 1), ('bwd_d', 'bwd', 0), ('bwd_e', 'bwd', 1)):
         out[name + '_ms_per_launch'] = timed(lambda: phase_loop(kind, phase)) / L
-    lib.gwtf_set_pdl(prev_pdl)
     del ybuf
     return out
 
 
-def nat_engine():
+def rate(points_per_s, flops_per_pt, peaks, fma_peak, passes):
+    """Roofline block of a whole pass: algorithmic TFLOP/s against the measured tensor peak for the precision tier
+    (`passes` TF32 MMAs per product) and against the FP32 FMA pipe."""
+    ach = points_per_s * flops_per_pt * 1e-12
+    tensor_peak = peaks['bf16_tflops'] / 2.0 / passes
+    return {'bound': 'tensor', 'achieved': ach, 'peak': tensor_peak, 'unit': 'TFLOP/s', 'frac': ach / tensor_peak,
+            'peak_source': 'MEASURED_PEAKS bf16_tflops %.1f / 2 (TF32) / %d (TF32 MMAs per product), of %s' %
+                           (peaks['bf16_tflops'], passes, peaks['source']),
+            'fma_peak': fma_peak, 'frac_of_fma_peak': ach / fma_peak, 'flops_per_point': flops_per_pt, 'traffic': None}
+
+
+def side_workloads(env, args, peaks, fma_peak):
+    """The other BASELINE configs, on every rank, aggregated over ranks."""
     from go_with_the_flows_b200 import _native as nat
-    return int(nat.lib().gwtf_engine())
-
-
-def side_workloads(model, cfg, dev, N):
-    """Other hot-path entry points (not the headline): fused eval-mode NLL (BASELINE configs[0] shape
-    at 64 clouds) and sampling (configs[3]/[4] shape: 256 latents x N points).  CUDA-event timed."""
+    from go_with_the_flows_b200 import flowstack
     from go_with_the_flows_b200.flowstack import sample_mixture
+    world, rank, dev = env.world, env.rank, env.dev
+    N = args.points
     out = {}
-    G = cfg['g_latent_space_size']
-    was_training = model.training
+    quick = args.quick
+
+    # ---- eval-mode NLL, airplane model, 64 clouds per GPU: fp32-grade and single-pass TF32
+    cfg, model = build_model('generative', dev)
     model.eval()
-    try:
-        with torch.no_grad():
-            p, g = synthetic(64, N, G, seed_shift=7)
-            p, g = p.to(dev), g.to(dev)
+    model.mode = 'training'
+    stack = model.flow_stack()
+    K, L, Fd = stack.K, stack.L, stack.F
+    fl_fwd, _ = flops_per_point(Fd, K, L)
+    p, g = synthetic(64, N, cfg['g_latent_space_size'], seed_shift=7 + rank)
+    p, g = p.to(dev), g.to(dev)
+    ev = {}
+    with torch.no_grad():
+        for tier, prec, passes in (('fp32_grade_3xtf32', nat.PRECISION_3XTF32, 3), ('tf32', nat.PRECISION_TF32, 1)):
+            stack.desc.eval_precision = prec
+            ms = env.timed(lambda: model.decode(p, g, N), reps=3)
+            pps = world * 64 * N / (ms * 1e-3)
+            ev[tier] = {'points_per_s': pps, 'ms': ms, 'clouds_per_gpu': 64, 'points': N,
+                        'roofline': rate(pps / world, fl_fwd, peaks, fma_peak, passes)}
+        stack.desc.eval_precision = flowstack._DEFAULTS['eval_precision']
+    out['eval_nll'] = ev
 
-            def timed(fn, reps=3):
-                fn()
-                torch.cuda.synchronize()
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record()
-                for _ in range(reps):
-                    fn()
-                e1.record()
-                torch.cuda.synchronize()
-                return e0.elapsed_time(e1) / reps
+    # ---- sampling sweep C5: airplane decoder, 256 latents per GPU
+    fl_samp = L * 4 * (Fd * Fd + 3 * Fd)
+    _, g2 = synthetic(256, 8, cfg['g_latent_space_size'], seed_shift=9 + rank)
+    g2 = g2.to(dev)
+    sweep = {}
+    with torch.no_grad():
+        logits = model.get_weights(g2)
+        mu_b, lv_b = model.base_gaussian(g2)
+        for tier, prec, passes in (('fp32_grade_3xtf32', nat.PRECISION_3XTF32, 3), ('tf32', nat.PRECISION_TF32, 1)):
+            stack.desc.eval_precision = prec
+            rows = {}
+            for n_pts in ((2048, 16384) if quick else (2048, 16384, 131072, 1048576)):
+                if tier == 'fp32_grade_3xtf32' and n_pts > 131072:
+                    continue
+                reps = 3 if n_pts <= 16384 else 1
+                ms = env.timed(lambda: sample_mixture(stack, g2, mu_b, lv_b, logits, n_pts, 2026, rank), reps=reps, flush=False)
+                pps = world * 256 * n_pts / (ms * 1e-3)
+                rows[str(n_pts)] = {'points_per_s': pps, 'ms': ms, 'roofline': rate(pps / world, fl_samp, peaks, fma_peak, passes)}
+                stack._keep_pool.clear()
+                torch.cuda.empty_cache()
+            sweep[tier] = rows
+        stack.desc.eval_precision = flowstack._DEFAULTS['eval_precision']
+        # B = 1 latency (the reference's evaluation loop samples shape by shape)
+        ms = env.timed(lambda: sample_mixture(stack, g2[:1], mu_b[:1], lv_b[:1], logits[:1], N, 2026, rank), reps=5, flush=False)
+        sweep['latency_1x%d_ms' % N] = ms
+    out['sampling_c5'] = {'latents_per_gpu': 256, 'decoder': 'airplane (K=4,L=33,F=37)', 'tiers': sweep}
+    del model, stack
+    torch.cuda.empty_cache()
 
-            ms = timed(lambda: model.decode(p, g, N))
-            out['eval_nll_fused'] = {'points_per_s': 64 * N / (ms * 1e-3), 'ms': ms, 'clouds': 64, 'points': N,
-                                     'kernel': 'per-layer tensor-core kernels, eval-mode BN (gwtf_nll_fwd_eval_layers)' if nat_engine() != 0 else 'k_nll_eval (one launch, fp32 FMA)'}
-            _, g2 = synthetic(256, N, G, seed_shift=9)
-            g2 = g2.to(dev)
-            stack = model.flow_stack()
-            logits = model.get_weights(g2)
-            mu_b, lv_b = model.base_gaussian(g2)
-            ms = timed(lambda: sample_mixture(stack, g2, mu_b, lv_b, logits, N, 2026, 0))
-            out['sampling'] = {'points_per_s': 256 * N / (ms * 1e-3), 'ms': ms, 'latents': 256, 'points': N,
-                               'kernel': 'Philox draws, points regrouped by component, per-layer tensor-core kernels in direct mode (gwtf_sample_layers)' if nat_engine() != 0 else 'k_sample (Philox draws + direct stacks, fp32 FMA)'}
-    finally:
-        model.train(was_training)
+    # ---- C4: config_SVR decoder (F=33, G=512, freevar), 256 x 2048 and 64 x 2500 (the config's cloud_size)
+    cfg4, model4 = build_model('svr', dev)
+    model4.eval()
+    model4.mode = 'reconstruction'
+    st4 = model4.flow_stack()
+    fl4 = st4.L * 4 * (st4.F * st4.F + 3 * st4.F)
+    c4 = {}
+    with torch.no_grad():
+        for tier, prec, passes in (('fp32_grade_3xtf32', nat.PRECISION_3XTF32, 3), ('tf32', nat.PRECISION_TF32, 1)):
+            st4.desc.eval_precision = prec
+            rows = {}
+            for Bs, n_pts in ((256, 2048), (64, 2500)):
+                _, g4 = synthetic(Bs, 8, cfg4['g_latent_space_size'], seed_shift=11 + rank)
+                g4 = g4.to(dev)
+                lg = model4.get_weights(g4)
+                mb, lb = model4.base_gaussian(g4)
+                ms = env.timed(lambda: sample_mixture(st4, g4, mb, lb, lg, n_pts, 2026, rank), reps=3, flush=False)
+                pps = world * Bs * n_pts / (ms * 1e-3)
+                rows['%dx%d' % (Bs, n_pts)] = {'points_per_s': pps, 'ms': ms,
+                                               'roofline': rate(pps / world, fl4, peaks, fma_peak, passes)}
+            c4[tier] = rows
+    out['sampling_c4'] = {'decoder': 'config_SVR (K=4,L=33,F=33,G=512)', 'tiers': c4}
+    del model4, st4
+    torch.cuda.empty_cache()
+
+    # ---- C3: config_autoencoding train step, 128 clouds per GPU
+    if not quick:
+        cfg3, model3 = build_model('autoencoding', dev)
+        model3.train()
+        model3.mode = 'training'
+        st3 = model3.flow_stack()
+        B3 = 128
+        p3, g3 = synthetic(B3, N, cfg3['g_latent_space_size'], seed_shift=13 + rank)
+        p3, g3 = p3.to(dev), g3.to(dev)
+        step3 = make_step(model3, world, N)
+        ms = env.timed(lambda: step3(p3, g3), reps=3, warmup=2)
+        _, fl3 = flops_per_point(st3.F, st3.K, st3.L)
+        pps = world * B3 * N / (ms * 1e-3)
+        out['c3_step'] = {'points_per_s': pps, 'ms_per_step': ms, 'clouds_per_gpu': B3,
+                          'workload': 'config_autoencoding (K=4,L=33,F=33,G=512,freevar), train-mode fwd+bwd',
+                          'roofline': rate(pps / world, fl3, peaks, fma_peak, 3)}
+        del model3, st3, step3
+        torch.cuda.empty_cache()
+
+    # ---- strong scaling at the reference's semantics: 64 clouds in total (train_ae.py:77-78)
+    if world > 1 and not quick:
+        cfgs, models = build_model('generative', dev)
+        models.train()
+        models.mode = 'training'
+        Bs = max(1, 64 // world)
+        ps, gs = synthetic(64, N, cfgs['g_latent_space_size'])
+        ps, gs = ps[rank * Bs:(rank + 1) * Bs].contiguous().to(dev), gs[rank * Bs:(rank + 1) * Bs].contiguous().to(dev)
+        steps_ = make_step(models, world, N)
+        ms = env.timed(lambda: steps_(ps, gs), reps=5, warmup=3)
+        _, fls = flops_per_point(models.flow_stack().F, models.flow_stack().K, models.flow_stack().L)
+        pps = world * Bs * N / (ms * 1e-3)
+        out['strong'] = {'points_per_s': pps, 'ms_per_step': ms, 'clouds_total': Bs * world, 'clouds_per_gpu': Bs,
+                         'scaling': 'strong', 'roofline': rate(pps / world, fls, peaks, fma_peak, 3)}
+        del models, steps_
+        torch.cuda.empty_cache()
     return out
 
 
@@ -307,6 +514,8 @@ def main():
     ap.add_argument('--batch', type=int, default=64, help='clouds per GPU')
     ap.add_argument('--points', type=int, default=2048)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-extra', action='store_true', help='headline only (skip the side workloads)')
+    ap.add_argument('--quick', action='store_true', help='shorter side workloads')
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference(args)
@@ -321,67 +530,39 @@ def main():
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
     args.warmup = max(args.warmup, 3)
+    env = Env(world, rank, dev)
 
     from go_with_the_flows_b200 import _native as nat
-    from go_with_the_flows_b200.networks.losses import FlowMixtureNLL
     cfg, model = build_model(args.config, dev)
     model.train()
     model.mode = 'training'
-    loss_fn = FlowMixtureNLL()
     stack = model.flow_stack()
     B, N, G = args.batch, args.points, cfg['g_latent_space_size']
     p_host, g_host = synthetic(B, N, G, seed_shift=rank)
     p_host, g_host = p_host.pin_memory(), g_host.pin_memory()
     p_dev, g_dev = p_host.to(dev), g_host.to(dev)
     loss_host = torch.zeros((), pin_memory=True)
-    params_all = [q for q in model.parameters()]
-    stack.prepare()
-    owned = set()
-    for name in stack.grad_masters:          # decoder tensors: averaged across ranks inside backward
-        owned.update(id(q) for q in stack.masters[name].params)
-    params_other = [q for q in params_all if id(q) not in owned]
-    flush_buf = torch.empty(256 * 1024 * 1024 // 4, device=dev)
-
-    def step(p, g):
-        for q in params_all:
-            q.grad = None
-        g = g.detach().requires_grad_(True)
-        out_dec, logits = model.decode(p, g, N)
-        pnll = loss_fn(out_dec, logits)
-        pnll.backward()
-        if world > 1:
-            grads = [q.grad for q in params_other if q.grad is not None]
-            flat = torch._utils._flatten_dense_tensors(grads)
-            dist.all_reduce(flat)
-            flat.div_(world)
-            for gr, fl in zip(grads, torch._utils._unflatten_dense_tensors(flat, grads)):
-                gr.copy_(fl)
-        return pnll
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    step = make_step(model, world, N)
 
     for _ in range(args.warmup):
         step(p_dev, g_dev)
-    barrier()
+    env.barrier()
 
     sampler = ClockSampler(local_rank)
     if rank == 0 and os.environ.get('GWTF_BENCH_NO_SAMPLER') != '1':
         sampler.start()
     # ---- device-resident timing: K steps, each bracketed by CUDA events, L2 flushed in between
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    barrier()
+    env.barrier()
     for e0, e1 in evs:
-        flush_buf.fill_(0.0)
+        env.flush_buf.fill_(0.0)
         e0.record()
         step(p_dev, g_dev)
         e1.record()
-    barrier()
-    dev_ms = sum(e0.elapsed_time(e1) for e0, e1 in evs)
+    env.barrier()
+    dev_ms = env.max_over_ranks(sum(e0.elapsed_time(e1) for e0, e1 in evs))
     # ---- end to end: pinned host inputs -> public API -> loss on the host, wall clock
-    barrier()
+    env.barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         p = p_host.to(dev, non_blocking=True)
@@ -389,15 +570,17 @@ def main():
         pnll = step(p, g)
         loss_host.copy_(pnll.detach(), non_blocking=True)
         torch.cuda.synchronize()
-    barrier()
-    e2e_ms = (time.perf_counter() - t0) * 1e3
+    env.barrier()
+    e2e_ms = env.max_over_ranks((time.perf_counter() - t0) * 1e3)
     clocks = sampler.stop() if rank == 0 else None
     loss_value = float(loss_host)
+    nonfinite = model.nonfinite_points()
 
-    t = torch.tensor([dev_ms, e2e_ms], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms = float(t[0]), float(t[1])
+    peaks = measured_peaks()
+    fma = ctypes.c_double(0.0)
+    nat.check(nat.lib().gwtf_fma_peak_tflops(20000, ctypes.byref(fma), None), 'gwtf_fma_peak_tflops')
+    fma_peak = fma.value
+    extra = None if args.no_extra else side_workloads(env, args, peaks, fma_peak)
 
     if rank == 0:
         K, L, Fd = stack.K, stack.L, stack.F
@@ -407,37 +590,34 @@ def main():
         value = pts_per_step / (ms_per_step * 1e-3)
         e2e_value = pts_per_step / (e2e_ms / args.steps * 1e-3)
         kt = kernel_only_times(model, p_dev, g_dev, reps=3)
-        peak = ctypes.c_double(0.0)
-        nat.check(nat.lib().gwtf_fma_peak_tflops(20000, ctypes.byref(peak), None), 'gwtf_fma_peak_tflops')
         mma_peak = ctypes.c_double(0.0)
         nat.check(nat.lib().gwtf_mma_peak_tflops(4000, ctypes.byref(mma_peak), None), 'gwtf_mma_peak_tflops')
-        engine = int(nat.lib().gwtf_engine())
+        fwd_eng, bwd_eng = stack.fwd_engine(), stack.bwd_engine()
         kept = bool(kt['kept'])
         kernel_ms = kt['fwd_ms'] + kt['bwd_ms']
         achieved = B * N * fl_step / (kernel_ms * 1e-3) * 1e-12
         per_pc_layer = 4 * (Fd * Fd + 3 * Fd)      # fwd FLOPs per point, component, layer
         launch_units = K * B * N
+        tensor_peak = peaks['bf16_tflops'] / 2.0 / 3.0          # dense TF32 = bf16 / 2; fp32-grade 3xTF32 = / 3
         # algorithmic share of each launch class (recomputation earns nothing)
         alg = {'fwd_stats': 0.0, 'fwd_apply': per_pc_layer * launch_units, 'bwd_d': 4 * Fd * 3 * launch_units,
                'bwd_e': (2 * per_pc_layer - 4 * Fd * 3) * launch_units}
-        # F x F contractions each launch class executes per point, component and net
-        executed = {'fwd_stats': 1, 'fwd_apply': 1, 'bwd_d': 0 if kept else 1, 'bwd_e': 2 if kept else 3}
+        names = {'fwd_stats': 'k_fwd_layer_tcp<..,0>', 'fwd_apply': 'k_fwd_layer_tcp<..,1>',
+                 'bwd_d': 'k_bwd_layer_tc<..,0>' if bwd_eng == nat.ENGINE_TC else 'k_bwd_layer_d_mma',
+                 'bwd_e': 'k_bwd_layer_tc<..,1>' if bwd_eng == nat.ENGINE_TC else 'k_bwd_layer_e_mma'}
         kernels = {}
         for name in ('fwd_stats', 'fwd_apply', 'bwd_d', 'bwd_e'):
             ms = kt[name + '_ms_per_launch']
-            kernels[name] = {'ms_per_launch': ms, 'algorithmic_tflops': alg[name] / (ms * 1e-3) * 1e-12,
-                             'executed_contractions': executed[name]}
-        # tensor-pipe work of the dominant kernel: m16n8k8 tf32 MMAs per 16-point tile and net (F padded to 8,
-        # the dW1 output to 16 rows), three per product (3xTF32)
-        f8, f16 = (Fd + 7) // 8, (Fd + 15) // 16
-        mma_per_tile = 3 * ((executed['bwd_e'] - 1) * f8 * f8 + 2 * f16 * f8)
-        e_tensor_tflops = mma_per_tile * 2048.0 * (launch_units / 16.0) * 2 / (kernels['bwd_e']['ms_per_launch'] * 1e-3) * 1e-12
+            tf = alg[name] / (ms * 1e-3) * 1e-12
+            kernels[name] = {'kernel': names[name], 'ms_per_launch': ms, 'share_of_step_kernels': ms * L / kernel_ms,
+                             'algorithmic_tflops': tf, 'frac': tf / tensor_peak, 'frac_of_fma_peak': tf / fma_peak}
+        dom_name = max(('fwd_stats', 'fwd_apply', 'bwd_d', 'bwd_e'), key=lambda n: kt[n + '_ms_per_launch'])
+        dom = kernels[dom_name]
         traffic = None
-        tpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'profiles', 'r01_ncu_traffic.json')
+        tpath = os.path.join(ROOT, 'profiles', 'r02_ncu_traffic.json')
         if os.path.exists(tpath) and args.config == 'generative' and B == 64 and N == 2048:
             with open(tpath) as fh:       # dram bytes per launch of the dominant kernel from the committed ncu capture
-                traffic = json.load(fh).get('k_bwd_layer_e_mma', {}).get('kept' if kept else 'recompute')
-        dom = kernels['bwd_e']
+                traffic = json.load(fh).get(dom['kernel'])
         line = {
             'metric': 'points/sec fwd+bwd mixture-flow NLL', 'value': value, 'unit': 'points/s', 'n_gpus': world,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True,
@@ -445,39 +625,36 @@ def main():
             'config': {'workload': workload_name(args), 'clouds_per_gpu': B, 'points_per_cloud': N,
                        'parallelism': 'dp%d (shapes sharded, SyncBN statistics + gradient all-reduce)' % world,
                        'l2': 'flushed between timed steps (256 MiB write outside the event bracket)',
-                       'bn': 'train mode (batch statistics)', 'loss': loss_value},
+                       'bn': 'train mode (batch statistics)', 'loss': loss_value, 'nonfinite_points': nonfinite},
             'e2e': {'value': e2e_value, 'unit': 'points/s', 'h2d_bytes_per_step': world * (p_host.numel() + g_host.numel()) * 4,
                     'd2h_bytes_per_step': world * 4, 'ms_per_step': e2e_ms / args.steps},
-            # our kernels per step: 4 layer phases x L, moments/bstat/nll/seed/finish, + one exchange kernel per phase at N > 1
+            # our kernels per step: 4 layer phases x L, moments/bstat/nll/seed/2 finish, + one exchange kernel per phase at N > 1
             'gpu_launches': args.steps * (4 * L + 6 + (4 * L if world > 1 else 0)),
             'roofline': {'bound': 'tensor',
-                         'kernel': 'k_bwd_layer_e_mma (dominant; per launch = one coupling layer, all K components)',
-                         'achieved': dom['algorithmic_tflops'], 'peak': mma_peak.value / 3.0, 'unit': 'TFLOP/s',
-                         'frac': dom['algorithmic_tflops'] / (mma_peak.value / 3.0), 'traffic': traffic,
-                         'peak_source': 'fp32-grade contractions run as 3xTF32 on mma.sync: peak = dense TF32 mma.sync '
-                                        'throughput measured live by gwtf_mma_peak_tflops (%.1f TFLOP/s) / 3; '
-                                        'MEASURED_PEAKS.json only holds the bf16 cuBLAS figure, which no fp32-parity '
-                                        'path can use' % mma_peak.value,
-                         'tensor_pipe': {'executed_tf32_tflops': e_tensor_tflops, 'mma_sync_tf32_peak': mma_peak.value,
-                                         'frac': e_tensor_tflops / mma_peak.value},
-                         'fma_peak': peak.value, 'frac_of_fma_peak': dom['algorithmic_tflops'] / peak.value,
+                         'kernel': '%s (dominant: %.0f %% of the step kernels; per launch = one coupling layer, all K '
+                                   'components)' % (dom['kernel'], 100 * dom['share_of_step_kernels']),
+                         'achieved': dom['algorithmic_tflops'], 'peak': tensor_peak, 'unit': 'TFLOP/s',
+                         'frac': dom['algorithmic_tflops'] / tensor_peak, 'traffic': traffic,
+                         'peak_source': 'MEASURED_PEAKS.json bf16_tflops %.1f (burst, of %s) / 2 (dense TF32 = half the bf16 '
+                                        'rate) / 3 (fp32-grade 3xTF32: three MMAs per product)' %
+                                        (peaks['bf16_tflops'], peaks['source']),
+                         'fma_peak': fma_peak, 'frac_of_fma_peak': dom['algorithmic_tflops'] / fma_peak,
+                         'diagnostic_mma_sync_tf32_peak': mma_peak.value,
                          'step': {'kernel_ms': kernel_ms, 'fwd_ms': kt['fwd_ms'], 'bwd_ms': kt['bwd_ms'],
-                                  'achieved': achieved, 'frac': achieved / (mma_peak.value / 3.0),
-                                  'frac_of_fma_peak': achieved / peak.value, 'flops_per_point': fl_step},
+                                  'achieved': achieved, 'frac': achieved / tensor_peak,
+                                  'frac_of_fma_peak': achieved / fma_peak, 'flops_per_point': fl_step,
+                                  'target': '>= 0.50 of the FP32-FMA roofline (north star)'},
                          'kernels': kernels},
             'clocks': clocks,
-            'engine': {0: 'fp32 FMA kernels',
-                       1: 'tcgen05 3xTF32 forward (one tile per CTA) + mma.sync 3xTF32 backward',
-                       2: 'tcgen05 3xTF32 persistent warp-specialised forward + mma.sync 3xTF32 backward',
-                       3: 'mma.sync 3xTF32 forward and backward'}[engine] +
-                      ('; sd1 outputs kept for backward (%.1f GB)' % (kt['kept_bytes'] / 1e9) if kept else '; backward recomputes h1') +
-                      '; fp32 FMA fused-eval / sampling kernels',
-            'extra': side_workloads(model, cfg, dev, N),
+            'engine': 'forward %s, backward %s%s' % (nat.ENGINE_NAMES[fwd_eng], nat.ENGINE_NAMES[bwd_eng],
+                                                     '; sd1 outputs kept for backward (%.1f GB)' % (kt['kept_bytes'] / 1e9)
+                                                     if kept else '; backward recomputes from the 12-byte layer inputs'),
+            'extra': extra,
         }
         if not args.no_cpu_baseline and world == 1:
             cb, cn = 4, N
-            sec, cores = oracle_step_time(args.config, cb, cn, 2, 1)
-            line['cpu_baseline'] = {'value': cb * cn / sec, 'unit': 'points/s', 'cores': cores, 'kind': 'port',
+            sec, cores, kind = cpu_step_time(args.config, cb, cn, 2, 1)
+            line['cpu_baseline'] = {'value': cb * cn / sec, 'unit': 'points/s', 'cores': cores, 'kind': kind,
                                     'sample': 'same model, train-mode fwd+bwd, %d clouds x %d points, 2 timed steps '
                                               'after 1 warm-up (%.2f s/step)' % (cb, cn, sec)}
         print(json.dumps(line), flush=True)

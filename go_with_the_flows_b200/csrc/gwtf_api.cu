@@ -520,12 +520,13 @@ int gwtf_sample(const gwtf_stack_desc* desc, const float* params, const float* b
 }
 
 static int64_t sample_npad(int K, int N) { return (int64_t)(N + 127) / 128 * 128 + 128 * (int64_t)K; }
+static int64_t up4(int64_t n) { return (n + 3) / 4 * 4; }      // 16-byte aligned sections (in 4-byte words)
 
 int64_t gwtf_sample_workspace_bytes(const gwtf_stack_desc* desc, int32_t B, int32_t N) {
     if (check_desc(desc) || B <= 0 || N <= 0) return 0;
     const int64_t K = desc->n_components, npad = sample_npad((int)K, N);
     // two ping-pong coordinate rows | slot (B,N) | counts, cursor (B,K) | seg (K,B,2) | seg_tiles (K,B+1)
-    return 4 * (2 * B * 3 * npad + (int64_t)B * N + 2 * B * K + 2 * K * B + K * (B + 1)) + 64;
+    return 4 * (2 * B * 3 * npad + up4((int64_t)B * N) + 2 * up4(B * K) + up4(2 * K * B) + up4(K * (B + 1))) + 64;
 }
 
 int gwtf_sample_layers(const gwtf_stack_desc* desc, const float* params, const float* bnbuf, const float* film,
@@ -544,10 +545,10 @@ int gwtf_sample_layers(const gwtf_stack_desc* desc, const float* params, const f
     const size_t row = (size_t)B * 3 * npad;
     float* xbuf = (float*)workspace;
     int32_t* slot = (int32_t*)(xbuf + 2 * row);
-    int32_t* counts = slot + (size_t)B * N;
-    int32_t* cursor = counts + (size_t)B * K;
-    int32_t* seg = cursor + (size_t)B * K;
-    int32_t* seg_tiles = seg + (size_t)2 * K * B;
+    int32_t* counts = slot + up4((int64_t)B * N);
+    int32_t* cursor = counts + up4((int64_t)B * K);
+    int32_t* seg = cursor + up4((int64_t)B * K);             // read as int2: needs 8-byte alignment
+    int32_t* seg_tiles = seg + up4((int64_t)2 * K * B);
     GWTF_CUDA(cudaMemsetAsync(counts, 0, sizeof(int32_t) * (size_t)B * K, st));
     const uint32_t seed_lo = (uint32_t)(seed & 0xFFFFFFFFull), sid = stream_id ^ (uint32_t)(seed >> 32);
     SamplePlanArgs pa;

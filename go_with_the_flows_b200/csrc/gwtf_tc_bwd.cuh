@@ -1,0 +1,764 @@
+// Backward of one coupling layer on the tcgen05 tensor cores (TMEM accumulators), same persistent warp-specialised
+// structure as the forward (gwtf_tc_persist.cuh): compute warpgroups (128 threads = 128 TMEM lanes = one 128-point
+// tile in flight each) + one MMA-issuer warp per tile slot, mbarrier hand-offs in both directions.
+// Same BwdArgs and outputs as the mma.sync kernels (gwtf_bwd_mma.cuh); math: SURVEY.md App. F.
+//
+// Phase 1 (k_bwd_layer_tc<.., 1>), per 128-point tile and net -- every contraction is a UMMA chain, 3xTF32:
+//   batch A   y0 = X B0^T                  (SS, K = 8: the (x,1 | dO) operand row of every point)
+//             P  = X PW^T                  dO (alpha W2): the sd2 backward with s/sigma1 folded in
+//   C0        a0 = relu(y0) -> TMEM operand (hi | lo), [y0 > 0] kept as a bit mask
+//   batch B   y1 = a0 B1^T                 (TS) sd1 + BN1 + FiLM folded into B1 (bias column): y1 leaves finished
+//   C1        r = [y1 > 0] P + beta y1 + gamma        = dh1 (BN1 backward is affine in y1; beta = gamma = 0 in eval)
+//             r -> TMEM operand AND, with a0, -> the point-contraction operands in shared memory (MN-major)
+//   batch C   da0 = r W1                   (TS)
+//             dW1 += r^T a0                (SS, K = the tile's 128 points, M = 64, accumulator resident in TMEM for the
+//                                           whole kernel; committed separately so the tile goes on while it runs)
+//   C2        dy0 = [y0 > 0] da0 -> TMEM operand; per-channel sums of dy0 (1, x_keep) by warp reduce-scatter
+//   batch D   du = dy0 Q0^T                (TS, N = 16): the input gradient
+// The two nets are processed one after the other (outer loop) so that one net's operands fit shared memory next to
+// the 128 KB of point-contraction operands, which the tile slots take turns on (sequence-numbered mbarrier).
+#pragma once
+#include "gwtf_tc_persist.cuh"
+#include "gwtf_bwd.cuh"
+
+namespace gwtf {
+
+constexpr int kBSlots = 2;
+constexpr int kBwdThreads = kBSlots * 128 + kBSlots * 32;      // compute warpgroups + one issuer warp per slot
+constexpr int kMnFloats = 2 * (128 / 4) * 128;                 // one MN-major operand: 2 atoms of 32 channels x 128 points
+
+__device__ __forceinline__ void bwd_compute_barrier() { asm volatile("bar.sync 2, %0;" ::"n"(kBSlots * 128) : "memory"); }
+__device__ __forceinline__ void wg_barrier(int slot) { asm volatile("bar.sync %0, 128;" ::"r"(3 + slot) : "memory"); }
+
+template <int FPK, int FPN>
+struct TcBwdECols {               // tensor-memory columns of one tile slot
+    static constexpr uint32_t D = 0, P = FPN, Ahi = 2 * FPN, Alo = 2 * FPN + FPK, SLOT = 2 * FPN + 2 * FPK;
+    static constexpr uint32_t G = kBSlots * SLOT;              // dW1 accumulators: FPK columns per slot (M = 64 rows)
+    static_assert(kBSlots * (SLOT + FPK) <= 512, "tensor memory budget");
+};
+
+template <int FPK, int FPN>
+struct TcBwdESmem {
+    LayerT<FPN> W;
+    LayerWB<FPN> WB;
+    TcOperand<FPN, 8> B0;          // [e][x0,x1,x2,1,0,0,0,0]        BN0-folded sd0 (+ bias); row F makes the constant one
+    TcOperand<FPN, 8> PW;          // [f][0,0,0,0,c2x,c2y,c2z,0]     c2 = (s/sigma1) * sd2 columns        (per shape)
+    TcOperand<FPN, FPK> B1;        // [f][e] folded sd1 | bias column                                       (per shape)
+    TcOperand<FPN, FPK> W1T;       // [e][f] = W1[f][e]
+    TcOperand<16, FPK> Q0;         // [d][e] = q0[e].d
+    float xd_hi[kBSlots][128 * 8], xd_lo[kBSlots][128 * 8];
+    float2 bg[FPN];                // (beta, gamma) of the current shape
+    float red[4 * 32];
+    uint64_t bar_tma, req[kBSlots], done[kBSlots], buf_free;
+    uint32_t tmem_base;
+};
+
+// D[M=64 x N] (+)= A^T B over the 128 points of a tile, both operands MN-major (sw32) in shared memory, 3xTF32
+template <int N>
+__device__ __forceinline__ void issue_point_contraction(uint32_t d_tmem, const float* a_hi, const float* a_lo,
+                                                        const float* b_hi, const float* b_lo) {
+    const uint32_t idesc = make_idesc_tf32(64, N, 1, 1);
+    const uint64_t ah = make_smem_desc_mnmajor_sw32(a_hi, 128), al = make_smem_desc_mnmajor_sw32(a_lo, 128);
+    const uint64_t bh = make_smem_desc_mnmajor_sw32(b_hi, 128), bl = make_smem_desc_mnmajor_sw32(b_lo, 128);
+#pragma unroll
+    for (int pass = 0; pass < 3; ++pass) {
+        const uint64_t a = pass == 1 ? al : ah;
+        const uint64_t b = pass == 2 ? bl : bh;
+#pragma unroll
+        for (int s = 0; s < 16; ++s)
+            mma_tf32_ss(d_tmem, a + (uint64_t)((s * 1024) >> 4), b + (uint64_t)((s * 1024) >> 4), idesc, true);
+    }
+}
+
+// this thread's 8 channels (one 32-byte chunk) of point `p` into an MN-major operand
+__device__ __forceinline__ void store_mn_chunk(float* arr, int chunk, int p, const float (&v)[8]) {
+    float* dst = arr + mnmajor_sw32_offset(8 * chunk, p, 128);
+    *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+
+template <int FPK, int FPN>
+__device__ __forceinline__ void bwd_tc_phase1(const BwdArgs& a, unsigned char* smem_raw) {
+    using SM = TcBwdESmem<FPK, FPN>;
+    using C = TcBwdECols<FPK, FPN>;
+    SM& S = *reinterpret_cast<SM*>(smem_raw);
+    float* raw = reinterpret_cast<float*>(smem_raw + round_up((int)sizeof(SM), 16));
+    const int F = a.d.n_features, K = a.d.n_components, L = a.d.n_layers;
+    // the point-contraction operands, 1024-byte aligned: r_hi | r_lo | a0_hi | a0_lo
+    float* mn = reinterpret_cast<float*>(
+        smem_raw + (((smem_u32(raw + round_up(raw_floats(F), 4)) + 1023u) & ~1023u) - smem_u32(smem_raw)));
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    const int slot = warp < kBSlots * 4 ? (warp >> 2) : kBSlots;
+    const int wtid = tid & 127;
+    const int j = blockIdx.y, l = a.layer;
+    const int N = a.N, B = a.B;
+    const bool train = a.train != 0;
+    constexpr int CT = kBSlots * 128;
+    const bool is_compute = slot < kBSlots;
+
+    LayerSrc src;
+    src.params = a.params + (size_t)(j * L + l) * a.d.rec_stride;
+    src.bn = a.bnbuf + (size_t)(j * L + l) * 8 * F;
+    src.film = nullptr;
+    src.mom = a.mom_in ? a.mom_in + j * GWTF_MOM_STRIDE : nullptr;
+    src.sum1 = a.sum1 ? a.sum1 + (size_t)j * 4 * F : nullptr;
+    src.n_total = a.n_total;
+
+    if (warp == kBSlots * 4) tmem_alloc(&S.tmem_base, 512);
+    if (tid == 0) {
+        mbar_init(&S.bar_tma, 1);
+        for (int s = 0; s < kBSlots; ++s) { mbar_init(&S.req[s], 128); mbar_init(&S.done[s], 1); }
+        mbar_init(&S.buf_free, 1);
+        mbar_fence_init();
+    }
+    for (int i = tid; i < kBSlots * 128 * 8; i += kBwdThreads) { (&S.xd_hi[0][0])[i] = 0.f; (&S.xd_lo[0][0])[i] = 0.f; }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    pdl_trigger();                    // only after this CTA owns its tensor-memory columns
+    if (tid == 0) issue_layer_copy(raw, src, F, !train, false, &S.bar_tma);
+    mbar_wait(&S.bar_tma, 0u);
+    pdl_wait();                       // phase 0 of this layer (its sums, dobuf, gbuf) is complete from here on
+    stage_vectors<FPN, true>(S.W, &S.WB, raw, src, F, a.d.warp_mask[l], train, false,
+                             train ? a.bsum + (size_t)j * 8 * F : nullptr, tid, kBwdThreads);
+    __syncthreads();
+
+    const unsigned wm = a.d.warp_mask[l];
+    const int w = popc3(wm), k = 3 - w;
+    const NetOffsets o = net_offsets(F, w);
+    int keepd[2];
+    keepd[0] = !(wm & 1u) ? 0 : (!(wm & 2u) ? 1 : 2);                        // first / second kept dimension
+    keepd[1] = k == 2 ? (!(wm & 4u) ? 2 : 1) : keepd[0];
+    float* dpr = a.dparams + (size_t)(j * L + l) * a.d.rec_stride;
+    double* bs = a.bsum + (size_t)j * 8 * F;
+    const uint32_t tbase = S.tmem_base;
+
+    const int tps = (N + 127) / 128;
+    const int total_tiles = B * tps;
+    const int per_cta = (total_tiles + gridDim.x - 1) / gridDim.x;
+    const int t_begin = min(blockIdx.x * per_cta, total_tiles), t_end = min(t_begin + per_cta, total_tiles);
+    const int my_tiles = t_end - t_begin;
+    const int rounds_n = (k + 1) * FPK <= 96 ? ((k + 1) * FPK <= 64 ? 2 : 3) : 4;    // reduce-scatter rounds of 32 values
+
+#pragma unroll 1
+    for (int net = 0; net < 2; ++net) {
+        // ---- operands of this net that do not depend on the shape
+        __syncthreads();              // everybody is done with the previous net's operands
+        for (int i = tid; i < FPN * 8; i += kBwdThreads) {                     // B0 (as stage_b0)
+            const int e = i >> 3, kk = i & 7;
+            float v = 0.f;
+            if (e < F) { const float4 q = S.W.q0[net][e]; v = kk == 0 ? q.x : (kk == 1 ? q.y : (kk == 2 ? q.z : (kk == 3 ? q.w : 0.f))); }
+            else if (e == F && kk == 3) v = 1.f;
+            S.B0.set(e, kk, v);
+        }
+        for (int i = tid; i < FPN * FPK; i += kBwdThreads) {                   // W1T[e][f] = W1[f][e]
+            const int e = i / FPK, f = i - e * FPK;
+            S.W1T.set(e, f, (e < F && f < F) ? raw[net * o.stride + o.W1 + f * F + e] : 0.f);
+        }
+        for (int i = tid; i < 16 * FPK; i += kBwdThreads) {                    // Q0[d][e] = q0[e].d
+            const int d = i / FPK, e = i - d * FPK;
+            float v = 0.f;
+            if (d < 3 && e < F) { const float4 q = S.W.q0[net][e]; v = d == 0 ? q.x : (d == 1 ? q.y : q.z); }
+            S.Q0.set(d, e, v);
+        }
+        for (int i = tid; i < 4 * 32; i += kBwdThreads) S.red[i] = 0.f;
+        if (is_compute) {                                                      // zero this slot's dW1 accumulator
+            float z[FPK];
+#pragma unroll
+            for (int i = 0; i < FPK; ++i) z[i] = 0.f;
+            tmem_st<FPK>(tbase + C::G + slot * FPK + ((uint32_t)((warp & 3) * 32) << 16), z);
+            tmem_wait_st();
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+
+        if (!is_compute) {
+            // ================= MMA issuer of slot s =================
+            const int s = warp - kBSlots * 4;
+            if (elect_one()) {
+                int tiles_s = 0;
+                {
+                    RoundIter it(t_begin, t_end, tps, nullptr, B);
+                    int base, count, b;
+                    while (it.next(base, count, b)) tiles_s += (s < count) ? 1 : 0;
+                }
+                uint32_t req_phase = (uint32_t)((net * tiles_s * 4 + net) & 1);  // 4 requests per tile (+1 drain per net)
+                const uint32_t ts = tbase + s * C::SLOT;
+                const uint32_t tg = tbase + C::G + s * FPK;
+#pragma unroll 1
+                for (int t = 0; t < tiles_s; ++t) {
+                    mbar_wait(&S.req[s], req_phase); req_phase ^= 1u; tc_fence_after();
+                    issue_ss_k8<FPN>(ts + C::D, S.xd_hi[s], S.xd_lo[s], S.B0.hi, S.B0.lo);
+                    issue_ss_k8<FPN>(ts + C::P, S.xd_hi[s], S.xd_lo[s], S.PW.hi, S.PW.lo);
+                    tc_commit(&S.done[s]);
+                    mbar_wait(&S.req[s], req_phase); req_phase ^= 1u; tc_fence_after();
+                    issue_ts<FPK, FPN>(ts + C::D, ts + C::Ahi, ts + C::Alo, S.B1.hi, S.B1.lo);
+                    tc_commit(&S.done[s]);
+                    mbar_wait(&S.req[s], req_phase); req_phase ^= 1u; tc_fence_after();
+                    issue_ts<FPK, FPN>(ts + C::D, ts + C::Ahi, ts + C::Alo, S.W1T.hi, S.W1T.lo);
+                    tc_commit(&S.done[s]);
+                    issue_point_contraction<FPK>(tg, mn, mn + kMnFloats, mn + 2 * kMnFloats, mn + 3 * kMnFloats);
+                    tc_commit(&S.buf_free);
+                    mbar_wait(&S.req[s], req_phase); req_phase ^= 1u; tc_fence_after();
+                    issue_ts<FPK, 16>(ts + C::D, ts + C::Ahi, ts + C::Alo, S.Q0.hi, S.Q0.lo);
+                    tc_commit(&S.done[s]);
+                }
+                // drain: everything this thread issued (its dW1 chain included) has completed
+                mbar_wait(&S.req[s], req_phase); tc_fence_after();
+                tc_commit(&S.done[s]);
+            }
+            __syncwarp();
+        } else {
+            // ================= compute warpgroups =================
+            const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
+            const uint32_t trow = tbase + slot * C::SLOT + lane_off;
+            uint64_t* req = &S.req[slot];
+            uint64_t* done = &S.done[slot];
+            // parities continue across the net loop: count what this slot did in the previous net
+            int tiles_s = 0;
+            {
+                RoundIter it0(t_begin, t_end, tps, nullptr, B);
+                int base, count, b;
+                while (it0.next(base, count, b)) tiles_s += (slot < count) ? 1 : 0;
+            }
+            uint32_t done_phase = (uint32_t)((net * tiles_s * 4 + net) & 1);
+            auto request = [&]() { tc_fence_before(); mbar_arrive(req); };
+            auto wait_done = [&]() { mbar_wait(done, done_phase); done_phase ^= 1u; tc_fence_after(); };
+            float sacc[4] = {0.f, 0.f, 0.f, 0.f};
+            int cur_b = -1;
+            int seq = net * my_tiles;              // sequence number of this CTA's point contractions (buffer turns)
+            RoundIter it(t_begin, t_end, tps, nullptr, B);
+            int base, count, b;
+            while (it.next(base, count, b)) {
+                if (b != cur_b) {
+                    // new shape: every warpgroup has drained the MMAs that read the per-shape operands
+                    bwd_compute_barrier();
+                    stage_film<FPN, true>(S.W, &S.WB, a.film + ((size_t)(b * K + j) * L + l) * 4 * F, F, tid, CT);
+                    bwd_compute_barrier();
+                    for (int i = tid; i < FPN * FPK; i += CT) {                // B1 (as stage_b1 with the FiLM fold)
+                        const int f = i / FPK, e = i - f * FPK;
+                        float v = 0.f;
+                        if (f < F) {
+                            if (e < F) v = S.W.st[net][f].x * raw[net * o.stride + o.W1 + f * F + e];
+                            else if (e == F) v = S.W.st[net][f].y;
+                        } else if (f == F && e == F) v = 1.f;
+                        S.B1.set(f, e, v);
+                    }
+                    for (int i = tid; i < FPN * 8; i += CT) {                  // PW[f][4+d] = (s/sigma1) w2[f].d
+                        const int f = i >> 3, kk = i & 7;
+                        float v = 0.f;
+                        if (f < F && kk >= 4 && kk < 7) {
+                            const float4 w2 = S.W.w2[net][f];
+                            v = S.W.st[net][f].x * (kk == 4 ? w2.x : (kk == 5 ? w2.y : w2.z));
+                        }
+                        S.PW.set(f, kk, v);
+                    }
+                    for (int f = tid; f < FPN; f += CT) {                      // dh1 = [y1>0] P + beta y1 + gamma
+                        float2 v = make_float2(0.f, 0.f);
+                        if (f < F && train) {
+                            const float s = S.WB.sg[net][f].x;
+                            const float tt = S.W.st[net][f].y + s * S.W.mi1[net][f].x;   // t = st.y + s mean1 istd1
+                            const float2 mi = S.W.mi1[net][f], ab = S.WB.ab1[net][f];
+                            v = make_float2(-mi.y * ab.y / s, mi.y * (ab.y * tt / s - ab.x));
+                        }
+                        S.bg[f] = v;
+                    }
+                    fence_proxy_async();
+                    bwd_compute_barrier();
+                    cur_b = b;
+                }
+                const int my_seq = seq + slot;
+                seq += count;
+                if (slot >= count) continue;
+                const int t = base + slot;
+                const int n = (t - it.shape_begin()) * 128 + wtid;
+                const bool valid = n < N;
+                const float* xin = a.xin_shared ? a.xin + (size_t)b * 3 * N : a.xin + ((size_t)j * B + b) * 3 * N;
+                const size_t sb = ((size_t)j * B + b) * 3 * N;
+                const float* dob = a.dobuf + ((size_t)j * B + b) * 6 * N + (size_t)net * 3 * N;
+                float x[3], dO[3], gold[3];
+#pragma unroll
+                for (int d = 0; d < 3; ++d) {
+                    x[d] = valid ? xin[(size_t)d * N + n] : 0.f;
+                    dO[d] = valid ? dob[(size_t)d * N + n] : 0.f;
+                    gold[d] = valid ? a.gbuf[sb + (size_t)d * N + n] : 0.f;
+                }
+                {   // the (x, 1 | dO) operand row of this point
+                    float h[6], lo[6];
+#pragma unroll
+                    for (int d = 0; d < 3; ++d) { split_tf32(x[d], h[d], lo[d]); split_tf32(dO[d], h[3 + d], lo[3 + d]); }
+                    const int off = kmajor_offset(wtid, 0, 8);
+                    *reinterpret_cast<float4*>(S.xd_hi[slot] + off) = make_float4(h[0], h[1], h[2], 1.0f);
+                    *reinterpret_cast<float4*>(S.xd_hi[slot] + off + 32) = make_float4(h[3], h[4], h[5], 0.0f);
+                    *reinterpret_cast<float4*>(S.xd_lo[slot] + off) = make_float4(lo[0], lo[1], lo[2], 0.0f);
+                    *reinterpret_cast<float4*>(S.xd_lo[slot] + off + 32) = make_float4(lo[3], lo[4], lo[5], 0.0f);
+                }
+                fence_proxy_async();
+                request();                                              // -> batch A: y0, P
+                wait_done();
+                uint32_t m0lo = 0u, m0hi = 0u;                          // [y0 > 0], channel c -> bit c
+#pragma unroll
+                for (int c = 0; c < FPK; c += 8) {
+                    float y[8], hi[8], lo[8];
+                    tmem_ld8(trow + C::D + c, y);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const bool pos = y[i] > 0.f;
+                        if (c + i < 32) m0lo |= pos ? (1u << (c + i)) : 0u; else m0hi |= pos ? (1u << (c + i - 32)) : 0u;
+                        split_tf32(fmaxf(y[i], 0.f), hi[i], lo[i]);
+                    }
+                    tmem_st8(trow + C::Ahi + c, hi);
+                    tmem_st8(trow + C::Alo + c, lo);
+                }
+                tmem_wait_st();
+                request();                                              // -> batch B: y1
+                // our turn on the point-contraction operands: contraction number my_seq - 1 has been consumed
+                if (my_seq > 0) mbar_wait(&S.buf_free, (uint32_t)((my_seq - 1) & 1));
+                wait_done();
+#pragma unroll
+                for (int c = 0; c < FPK; c += 8) {
+                    float y1[8], p8[8], ah[8], al[8], rh[8], rl[8];
+                    tmem_ld8(trow + C::D + c, y1);
+                    tmem_ld8(trow + C::P + c, p8);
+                    tmem_ld8(trow + C::Ahi + c, ah);
+                    tmem_ld8(trow + C::Alo + c, al);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int i = 0; i < 8; i += 2) {
+                        const float4 g2 = *reinterpret_cast<const float4*>(&S.bg[c + i]);      // (beta, gamma) x 2
+                        float r0 = fmaf(g2.x, y1[i], g2.y) + (y1[i] > 0.f ? p8[i] : 0.f);
+                        float r1 = fmaf(g2.z, y1[i + 1], g2.w) + (y1[i + 1] > 0.f ? p8[i + 1] : 0.f);
+                        if (!valid) { r0 = 0.f; r1 = 0.f; }
+                        split_tf32(r0, rh[i], rl[i]);
+                        split_tf32(r1, rh[i + 1], rl[i + 1]);
+                    }
+                    tmem_st8(trow + C::Ahi + c, rh);
+                    tmem_st8(trow + C::Alo + c, rl);
+                    store_mn_chunk(mn, c >> 3, wtid, rh);
+                    store_mn_chunk(mn + kMnFloats, c >> 3, wtid, rl);
+                    store_mn_chunk(mn + 2 * kMnFloats, c >> 3, wtid, ah);
+                    store_mn_chunk(mn + 3 * kMnFloats, c >> 3, wtid, al);
+                }
+                tmem_wait_st();
+                fence_proxy_async();
+                request();                                              // -> batch C: da0, then dW1 += r^T a0
+                wait_done();                                            // (da0 only: dW1 keeps running)
+                {
+                    float v[32];
+                    const float xa = keepd[0] == 0 ? x[0] : (keepd[0] == 1 ? x[1] : x[2]);
+                    const float xb = keepd[1] == 0 ? x[0] : (keepd[1] == 1 ? x[1] : x[2]);
+                    // dy0 = [y0 > 0] da0 -> operand; values (dy0 | dy0 xa | dy0 xb) reduced over the warp's 32 points
+                    float dy[FPK];
+#pragma unroll
+                    for (int c = 0; c < FPK; c += 8) {
+                        float d8[8], hi[8], lo[8];
+                        tmem_ld8(trow + C::D + c, d8);
+                        tmem_wait_ld();
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const bool pos = (c + i < 32) ? ((m0lo >> (c + i)) & 1u) : ((m0hi >> (c + i - 32)) & 1u);
+                            dy[c + i] = pos ? d8[i] : 0.f;
+                            split_tf32(dy[c + i], hi[i], lo[i]);
+                        }
+                        tmem_st8(trow + C::Ahi + c, hi);
+                        tmem_st8(trow + C::Alo + c, lo);
+                    }
+                    tmem_wait_st();
+                    request();                                          // -> batch D: du
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        if (r < rounds_n) {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) {
+                                const int vi = 32 * r + i, wsel = vi / FPK, e = vi - wsel * FPK;
+                                v[i] = wsel == 0 ? dy[e] : (wsel == 1 ? dy[e] * xa : (wsel == 2 ? dy[e] * xb : 0.f));
+                            }
+                            sacc[r] += warp_reduce_scatter32(v, lane);
+                        }
+                    }
+                }
+                wait_done();
+                {
+                    float du[8];
+                    tmem_ld8(trow + C::D, du);
+                    tmem_wait_ld();
+                    if (valid) {
+#pragma unroll
+                        for (int d = 0; d < 3; ++d) a.gbuf[sb + (size_t)d * N + n] = gold[d] + du[d];
+                    }
+                }
+            }
+            // ---- drain this slot's MMAs (the dW1 chain of the last tile included)
+            request();
+            wait_done();
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+                if (r < rounds_n) atomicAdd(&S.red[32 * r + lane], sacc[r]);
+        }
+        __syncthreads();
+        // ---- flush the per-channel sums of this net: dbeta0 = S1, dW0 raw sums, dgamma0 = r0 . (Sx, S1)
+        for (int e = tid; e < F; e += kBwdThreads) {
+            const float s1 = S.red[e], sa = S.red[FPK + e], sbv = k == 2 ? S.red[2 * FPK + e] : 0.f;
+            const float4 rv = S.WB.r0[net][e];
+            const float ra = keepd[0] == 0 ? rv.x : (keepd[0] == 1 ? rv.y : rv.z);
+            const float rb = k == 2 ? (keepd[1] == 0 ? rv.x : (keepd[1] == 1 ? rv.y : rv.z)) : 0.f;
+            const float dg = fmaf(ra, sa, fmaf(rb, sbv, rv.w * s1));
+            atomicAdd(&dpr[net * o.stride + o.g0 + e], dg);
+            atomicAdd(&bs[(net * 4 + 3) * F + e], (double)dg);
+            atomicAdd(&dpr[net * o.stride + o.b0 + e], s1);
+            atomicAdd(&bs[(net * 4 + 2) * F + e], (double)s1);
+            atomicAdd(&dpr[net * o.stride + o.W0 + e * k + 0], sa);
+            if (k == 2) atomicAdd(&dpr[net * o.stride + o.W0 + e * k + 1], sbv);
+        }
+        // ---- flush dW1: the M = 64 accumulator keeps row f in lane 32 (f / 16) + f % 16
+        if (is_compute) {
+            const int f = (warp & 3) * 16 + (wtid & 31);
+            float g[FPK];
+            tmem_ld<FPK>(tbase + C::G + slot * FPK + ((uint32_t)((warp & 3) * 32) << 16), g);
+            tmem_wait_ld();
+            if ((wtid & 31) < 16 && f < F) {
+#pragma unroll
+                for (int e = 0; e < FPK; ++e)
+                    if (e < F) atomicAdd(&dpr[net * o.stride + o.W1 + f * F + e], g[e]);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == kBSlots * 4) tmem_dealloc(tbase, 512);
+}
+
+// =============================================================================================
+// Phase 0 (k_bwd_layer_tc<.., 0>): d(o_mu, o_lv) of every point, FiLM / sd2 gradients, sd1_bn backward sums.
+// Per tile and net (logvar net first: its head fixes sigma, hence dO of both nets):
+//   batch A   y0 = X B0^T  ->  a0 = relu(y0)                      batch B   y1 = a0 B1^T  (folded)
+//   logvar net only:  a1 = relu(y1) -> batch C   o = a1 B2^T (N = 16)  -> softsign / sigma / dO, written to dobuf, gbuf
+//   sums over points of dO_d a1 and dO_d [y1 > 0] for the warped dims d (warp reduce-scatter, per-shape accumulators):
+//     dW2 = sum dO a1;   dt = sum_d W2_d sum dO_d [y1>0];   ds = (sum_d W2_d sum dO_d a1 - t dt) / s     (a1 = [y1>0] y1)
+//   so the CUDA cores never form da1 = W2^T dO per point and never touch a per-channel constant in the tile loop.
+// =============================================================================================
+constexpr int kDSlots = 3;
+constexpr int kBwdDThreads = kDSlots * 128 + kDSlots * 32;
+constexpr int kDRounds = 5;                                     // reduce-scatter rounds of 32 values (<= 4 FPK + 4 values)
+
+__device__ __forceinline__ void bwd_d_barrier() { asm volatile("bar.sync 2, %0;" ::"n"(kDSlots * 128) : "memory"); }
+
+template <int FPK, int FPN>
+struct TcBwdDSmem {
+    LayerT<FPN> W;
+    LayerWB<FPN> WB;
+    TcLayerOps<FPK, FPN> ops;      // B0 | B1 (folded, per shape) | B2 of the current net
+    float x_hi[kDSlots][128 * 8], x_lo[kDSlots][128 * 8];
+    float corr[12];
+    float red[kDRounds * 32];
+    uint64_t bar_tma, req[kDSlots], done[kDSlots];
+    uint32_t tmem_base;
+};
+
+template <int FPK, int FPN>
+__device__ __forceinline__ void bwd_tc_phase0(const BwdArgs& a, unsigned char* smem_raw) {
+    using SM = TcBwdDSmem<FPK, FPN>;
+    using C = TcCols<FPK, FPN>;
+    SM& S = *reinterpret_cast<SM*>(smem_raw);
+    float* raw = reinterpret_cast<float*>(smem_raw + round_up((int)sizeof(SM), 16));
+    const int F = a.d.n_features, K = a.d.n_components, L = a.d.n_layers;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    const int slot = warp < kDSlots * 4 ? (warp >> 2) : kDSlots;
+    const int wtid = tid & 127;
+    const int j = blockIdx.y, l = a.layer;
+    const int N = a.N, B = a.B;
+    const bool train = a.train != 0;
+    constexpr int CT = kDSlots * 128;
+    const bool is_compute = slot < kDSlots;
+
+    LayerSrc src;
+    src.params = a.params + (size_t)(j * L + l) * a.d.rec_stride;
+    src.bn = a.bnbuf + (size_t)(j * L + l) * 8 * F;
+    src.film = nullptr;
+    src.mom = a.mom_in ? a.mom_in + j * GWTF_MOM_STRIDE : nullptr;
+    src.sum1 = a.sum1 ? a.sum1 + (size_t)j * 4 * F : nullptr;
+    src.n_total = a.n_total;
+
+    if (warp == kDSlots * 4) tmem_alloc(&S.tmem_base, 512);
+    if (tid == 0) {
+        mbar_init(&S.bar_tma, 1);
+        for (int s = 0; s < kDSlots; ++s) { mbar_init(&S.req[s], 128); mbar_init(&S.done[s], 1); }
+        mbar_fence_init();
+    }
+    for (int i = tid; i < kDSlots * 128 * 8; i += kBwdDThreads) { (&S.x_hi[0][0])[i] = 0.f; (&S.x_lo[0][0])[i] = 0.f; }
+    if (tid < 12) S.corr[tid] = 0.f;
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    pdl_trigger();
+    if (tid == 0) issue_layer_copy(raw, src, F, !train, false, &S.bar_tma);
+    mbar_wait(&S.bar_tma, 0u);
+    pdl_wait();                       // the previous layer's phase 1 (its gbuf, bn0 sums) is complete from here on
+    const bool correct = train && a.mom_prev != nullptr;
+    if (correct)
+        bn0_correction<FPN>(a.d, a.params, j, l - 1, a.mom_prev + j * GWTF_MOM_STRIDE, a.bsum_prev + (size_t)j * 8 * F,
+                            a.n_total, S.corr, tid);
+    stage_vectors<FPN, true>(S.W, &S.WB, raw, src, F, a.d.warp_mask[l], train, false, nullptr, tid, kBwdDThreads);
+    __syncthreads();
+    float Mc[12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) Mc[i] = correct ? S.corr[i] : 0.f;
+
+    const unsigned wm = a.d.warp_mask[l];
+    const int w = popc3(wm);
+    const NetOffsets o = net_offsets(F, w);
+    int wd[2];                                                   // first / second warped dimension
+    wd[0] = (wm & 1u) ? 0 : ((wm & 2u) ? 1 : 2);
+    wd[1] = w == 2 ? ((wm & 4u) ? 2 : 1) : wd[0];
+    const int n_vals = 2 * w * FPK + w;                          // (a1 dO_d | [y1>0] dO_d) per channel, then the bias sums
+    const int rounds_n = (n_vals + 31) / 32;
+    float* dpr = a.dparams + (size_t)(j * L + l) * a.d.rec_stride;
+    double* bs = a.bsum + (size_t)j * 8 * F;
+    const uint32_t tbase = S.tmem_base;
+
+    const int tps = (N + 127) / 128;
+    const int total_tiles = B * tps;
+    const int per_cta = (total_tiles + gridDim.x - 1) / gridDim.x;
+    const int t_begin = min(blockIdx.x * per_cta, total_tiles), t_end = min(t_begin + per_cta, total_tiles);
+
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {
+        const int net = 1 - pass;                                // the logvar net first
+        const int stages = net == 1 ? 3 : 2;                     // MMA batches per tile
+        __syncthreads();
+        stage_b0<FPK, FPN>(S.ops, S.W.q0[net], F, tid, kBwdDThreads);
+        stage_b2<FPK, FPN>(S.ops, S.W.w2[net], S.W.b2[net], F, tid, kBwdDThreads);
+        for (int i = tid; i < kDRounds * 32; i += kBwdDThreads) S.red[i] = 0.f;
+        fence_proxy_async();
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+
+        // how many requests each slot made in the first pass (3 per tile + drain): barrier parities go on from there
+        auto tiles_of = [&](int s) {
+            int n = 0;
+            RoundIter it0(t_begin, t_end, tps, nullptr, B);
+            int base, count, b;
+            while (it0.next(base, count, b)) n += (s < count) ? 1 : 0;
+            return n;
+        };
+
+        if (!is_compute) {
+            const int s = warp - kDSlots * 4;
+            if (elect_one()) {
+                const int tiles_s = tiles_of(s);
+                uint32_t req_phase = pass == 0 ? 0u : (uint32_t)((tiles_s * 3 + 1) & 1);
+                const uint32_t ts = tbase + s * kTcCols;
+#pragma unroll 1
+                for (int t = 0; t < tiles_s; ++t) {
+                    mbar_wait(&S.req[s], req_phase); req_phase ^= 1u; tc_fence_after();
+                    issue_ss_k8<FPN>(ts + C::D, S.x_hi[s], S.x_lo[s], S.ops.B0.hi, S.ops.B0.lo);
+                    tc_commit(&S.done[s]);
+                    mbar_wait(&S.req[s], req_phase); req_phase ^= 1u; tc_fence_after();
+                    issue_ts<FPK, FPN>(ts + C::D, ts + C::Ahi, ts + C::Alo, S.ops.B1.hi, S.ops.B1.lo);
+                    tc_commit(&S.done[s]);
+                    if (stages == 3) {
+                        mbar_wait(&S.req[s], req_phase); req_phase ^= 1u; tc_fence_after();
+                        issue_ts<FPK, 16>(ts + C::D, ts + C::Ahi, ts + C::Alo, S.ops.B2.hi, S.ops.B2.lo);
+                        tc_commit(&S.done[s]);
+                    }
+                }
+                mbar_wait(&S.req[s], req_phase); tc_fence_after();      // drain
+                tc_commit(&S.done[s]);
+            }
+            __syncwarp();
+        } else {
+            const uint32_t trow = tbase + slot * kTcCols + ((uint32_t)((warp & 3) * 32) << 16);
+            uint64_t* req = &S.req[slot];
+            uint64_t* done = &S.done[slot];
+            uint32_t done_phase = pass == 0 ? 0u : (uint32_t)((tiles_of(slot) * 3 + 1) & 1);
+            auto request = [&]() { tc_fence_before(); mbar_arrive(req); };
+            auto wait_done = [&]() { mbar_wait(done, done_phase); done_phase ^= 1u; tc_fence_after(); };
+            float sacc[kDRounds];
+#pragma unroll
+            for (int r = 0; r < kDRounds; ++r) sacc[r] = 0.f;
+
+            auto flush_shape = [&](int b) {
+                // per-shape sums -> block partials -> FiLM / sd2 gradients and the sd1_bn backward sums
+#pragma unroll
+                for (int r = 0; r < kDRounds; ++r) {
+                    if (r < rounds_n) atomicAdd(&S.red[32 * r + lane], sacc[r]);
+                    sacc[r] = 0.f;
+                }
+                bwd_d_barrier();
+                float* dfl = a.dfilm + ((size_t)(b * K + j) * L + l) * 4 * F;
+                for (int f = tid; f < F; f += CT) {
+                    const float4 w2 = S.W.w2[net][f];
+                    const float s = S.WB.sg[net][f].x;
+                    const float tt = S.W.st[net][f].y + s * S.W.mi1[net][f].x;
+                    float Asum = 0.f, dt = 0.f;
+                    for (int q = 0; q < w; ++q) {
+                        const float wq = wd[q] == 0 ? w2.x : (wd[q] == 1 ? w2.y : w2.z);
+                        const float sa = S.red[q * FPK + f], sm = S.red[(w + q) * FPK + f];
+                        Asum = fmaf(wq, sa, Asum);
+                        dt = fmaf(wq, sm, dt);
+                        atomicAdd(&dpr[net * o.stride + o.W2 + q * F + f], sa);
+                    }
+                    const float ds = (Asum - tt * dt) / s;
+                    atomicAdd(&dfl[net * 2 * F + f], ds);
+                    atomicAdd(&dfl[net * 2 * F + F + f], dt);
+                    if (train) {
+                        atomicAdd(&bs[(net * 4 + 1) * F + f], (double)(ds * s));
+                        atomicAdd(&bs[(net * 4 + 0) * F + f], (double)(dt * s));
+                    }
+                }
+                if (tid < w) atomicAdd(&dpr[net * o.stride + o.b2 + tid], S.red[2 * w * FPK + tid]);
+                bwd_d_barrier();
+                for (int i = tid; i < kDRounds * 32; i += CT) S.red[i] = 0.f;
+            };
+
+            int cur_b = -1;
+            RoundIter it(t_begin, t_end, tps, nullptr, B);
+            int base, count, b;
+            while (it.next(base, count, b)) {
+                if (b != cur_b) {
+                    if (cur_b >= 0) flush_shape(cur_b);
+                    bwd_d_barrier();
+                    stage_film<FPN, true>(S.W, &S.WB, a.film + ((size_t)(b * K + j) * L + l) * 4 * F, F, tid, CT);
+                    bwd_d_barrier();
+                    stage_b1<FPK, FPN>(S.ops, raw + net * o.stride + o.W1, S.W.st[net], F, tid, CT);
+                    fence_proxy_async();
+                    bwd_d_barrier();
+                    cur_b = b;
+                }
+                if (slot >= count) continue;
+                const int t = base + slot;
+                const int n = (t - it.shape_begin()) * 128 + wtid;
+                const bool valid = n < N;
+                const float* xin = a.xin_shared ? a.xin + (size_t)b * 3 * N : a.xin + ((size_t)j * B + b) * 3 * N;
+                const size_t sb = ((size_t)j * B + b) * 3 * N;
+                float* dob = a.dobuf + ((size_t)j * B + b) * 6 * N;
+                float x[3];
+#pragma unroll
+                for (int d = 0; d < 3; ++d) x[d] = valid ? xin[(size_t)d * N + n] : 0.f;
+                float outv[3] = {0.f, 0.f, 0.f}, gc[3] = {0.f, 0.f, 0.f}, gsv[3] = {0.f, 0.f, 0.f}, dO[3] = {0.f, 0.f, 0.f};
+                if (net == 1) {
+                    if (valid) {
+                        float g0[3];
+#pragma unroll
+                        for (int d = 0; d < 3; ++d) {
+                            outv[d] = a.xout[sb + (size_t)d * N + n];
+                            g0[d] = a.gbuf[sb + (size_t)d * N + n];
+                            gsv[d] = a.gs[sb + (size_t)d * N + n];
+                        }
+#pragma unroll
+                        for (int d = 0; d < 3; ++d)        // lazy bn0 correction of the layer processed before this one
+                            gc[d] = g0[d] - (Mc[d * 3] * outv[0] + Mc[d * 3 + 1] * outv[1] + Mc[d * 3 + 2] * outv[2]) + Mc[9 + d];
+                    }
+                } else if (valid) {
+#pragma unroll
+                    for (int d = 0; d < 3; ++d) dO[d] = dob[(size_t)d * N + n];
+                }
+                write_x_operand(S.x_hi[slot], S.x_lo[slot], x, wtid);
+                fence_proxy_async();
+                request();                                              // -> y0
+                wait_done();
+                relu_to_operand<FPK, FPN>(trow);
+                request();                                              // -> y1
+                wait_done();
+                float y1[FPK];
+                tmem_ld<FPK>(trow + C::D, y1);
+                tmem_wait_ld();
+                if (net == 1) {
+                    // head of the logvar net on the tensor core: a1 -> operand, o = a1 B2^T
+#pragma unroll
+                    for (int c = 0; c < FPK; c += 8) {
+                        float hi[8], lo[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) split_tf32(fmaxf(y1[c + i], 0.f), hi[i], lo[i]);
+                        tmem_st8(trow + C::Ahi + c, hi);
+                        tmem_st8(trow + C::Alo + c, lo);
+                    }
+                    tmem_wait_st();
+                    request();                                          // -> o
+                    wait_done();
+                    float ov[8];
+                    tmem_ld8(trow + C::D, ov);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int d = 0; d < 3; ++d) {
+                        const float olv = ov[d];
+                        const float lam = softsign(olv);
+                        const float ex = expf(lam);
+                        const float sig2 = GWTF_FLOW_EPS + ex;
+                        const float sig = sqrtf(sig2);
+                        const float gin = gc[d] / sig;
+                        const float dlam = gsv[d] - gc[d] * outv[d] * ex / (2.0f * sig2);
+                        const float den = 1.0f + fabsf(olv);
+                        const float dov = valid ? dlam / (den * den) : 0.f;
+                        if (valid) {
+                            a.gbuf[sb + (size_t)d * N + n] = gin;
+                            dob[(size_t)d * N + n] = -gin;
+                            dob[(size_t)(3 + d) * N + n] = dov;
+                        }
+                        dO[d] = dov;
+                    }
+                }
+                // ---- sums over the warp's 32 points
+                const float dA = wd[0] == 0 ? dO[0] : (wd[0] == 1 ? dO[1] : dO[2]);
+                const float dB = wd[1] == 0 ? dO[0] : (wd[1] == 1 ? dO[1] : dO[2]);
+#pragma unroll
+                for (int r = 0; r < kDRounds; ++r) {
+                    if (r < rounds_n) {
+                        float v[32];
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            const int vi = 32 * r + i;
+                            // w = 1: [a1 dA | m dA | dA];   w = 2: [a1 dA | a1 dB | m dA | m dB | dA dB]
+                            const int q = vi / FPK, e = vi - q * FPK;
+                            float val = 0.f;
+                            if (q < 4) {
+                                const float yv = y1[e];
+                                const bool is_a = w == 1 ? (q == 0) : (q < 2);
+                                const bool use = w == 1 ? (q < 2) : true;
+                                const float dsel = w == 1 ? dA : ((q & 1) ? dB : dA);
+                                val = use ? (is_a ? fmaxf(yv, 0.f) * dsel : (yv > 0.f ? dsel : 0.f)) : 0.f;
+                                if (w == 1 && q == 2 && e == 0) val = dA;
+                            } else if (w == 2) {
+                                if (vi == 4 * FPK) val = dA; else if (vi == 4 * FPK + 1) val = dB;
+                            }
+                            v[i] = val;
+                        }
+                        sacc[r] += warp_reduce_scatter32(v, lane);
+                    }
+                }
+            }
+            if (cur_b >= 0) flush_shape(cur_b);
+            request();                                                  // drain
+            wait_done();
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == kDSlots * 4) tmem_dealloc(tbase, 512);
+}
+
+template <int FPK, int FPN>
+__host__ __device__ constexpr size_t bwd_tc_d_smem(int F) {
+    return round_up((int)sizeof(TcBwdDSmem<FPK, FPN>), 16) + (size_t)round_up(raw_floats(F), 4) * 4;
+}
+
+template <int FPK, int FPN>
+__host__ __device__ constexpr size_t bwd_tc_smem(int F) {
+    return round_up((int)sizeof(TcBwdESmem<FPK, FPN>), 16) + (size_t)round_up(raw_floats(F), 4) * 4 + 1024 +
+           4 * (size_t)kMnFloats * 4;
+}
+
+template <int FPK, int FPN, int PHASE>
+__global__ void __launch_bounds__(PHASE == 0 ? kBwdDThreads : kBwdThreads, 1) k_bwd_layer_tc(const BwdArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    if constexpr (PHASE == 0) bwd_tc_phase0<FPK, FPN>(a, smem_raw);
+    else bwd_tc_phase1<FPK, FPN>(a, smem_raw);
+}
+
+}  // namespace gwtf

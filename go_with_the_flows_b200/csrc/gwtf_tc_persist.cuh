@@ -84,7 +84,10 @@ __global__ void __launch_bounds__(kPersistThreads, 1) k_fwd_layer_tcp(const Laye
     SM& S = *reinterpret_cast<SM*>(smem_raw);
     float* raw = reinterpret_cast<float*>(smem_raw + round_up((int)sizeof(SM), 16));
     const int F = a.d.n_features, K = a.d.n_components, L = a.d.n_layers;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
+    // the warp index through a shuffle: the compiler then knows it is warp-uniform and keeps everything the MMA
+    // issuer derives from it (tensor-memory addresses, shared-memory descriptors) in uniform registers
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     const int slot = warp < kSlots * 4 ? (warp >> 2) : kSlots;   // 0..3 compute warpgroups, 4 = issuer warps
     const int wtid = tid & 127;                         // thread within its warpgroup = TMEM lane
     const int j = blockIdx.y, l = a.layer;
@@ -144,8 +147,11 @@ __global__ void __launch_bounds__(kPersistThreads, 1) k_fwd_layer_tcp(const Laye
 
     if (!is_compute) {
         // ================= MMA issuers: warp (16 + s) serves slot s =================
+        // One elected thread per issuer warp (elect.sync, not `lane == 0`: with a data-dependent lane test the compiler
+        // re-materialises every descriptor through R2UR and a single thread then issues one tcgen05.mma per ~125
+        // cycles; elected, the same loop issues them back to back at the tensor pipe's own rate -- tools/tc_probe4.cu)
         const int s = warp - kSlots * 4;
-        if (lane == 0) {
+        if (elect_one()) {
             int remaining = 0;
             {
                 RoundIter it(t_begin, t_end, a.tiles_per_shape, pre, B);
