@@ -443,7 +443,7 @@ __device__ __forceinline__ void bwd_tc_phase1(const BwdArgs& a, unsigned char* s
 // =============================================================================================
 constexpr int kDSlots = 3;
 constexpr int kBwdDThreads = kDSlots * 128 + kDSlots * 32;
-constexpr int kDRounds = 5;                                     // reduce-scatter rounds of 32 values (<= 4 FPK + 4 values)
+constexpr int kDRounds = 5;                                     // reduce-scatter rounds of 32 values (<= 4 FPK values)
 
 __device__ __forceinline__ void bwd_d_barrier() { asm volatile("bar.sync 2, %0;" ::"n"(kDSlots * 128) : "memory"); }
 
@@ -515,7 +515,7 @@ __device__ __forceinline__ void bwd_tc_phase0(const BwdArgs& a, unsigned char* s
     int wd[2];                                                   // first / second warped dimension
     wd[0] = (wm & 1u) ? 0 : ((wm & 2u) ? 1 : 2);
     wd[1] = w == 2 ? ((wm & 4u) ? 2 : 1) : wd[0];
-    const int n_vals = 2 * w * FPK + w;                          // (a1 dO_d | [y1>0] dO_d) per channel, then the bias sums
+    const int n_vals = 2 * w * FPK;                              // (a1 dO_d | [y1>0] dO_d) per channel and warped dim
     const int rounds_n = (n_vals + 31) / 32;
     float* dpr = a.dparams + (size_t)(j * L + l) * a.d.rec_stride;
     double* bs = a.bsum + (size_t)j * 8 * F;
@@ -612,7 +612,7 @@ __device__ __forceinline__ void bwd_tc_phase0(const BwdArgs& a, unsigned char* s
                         atomicAdd(&bs[(net * 4 + 0) * F + f], (double)(dt * s));
                     }
                 }
-                if (tid < w) atomicAdd(&dpr[net * o.stride + o.b2 + tid], S.red[2 * w * FPK + tid]);
+                if (tid < w) atomicAdd(&dpr[net * o.stride + o.b2 + tid], S.red[tid * FPK + F]);
                 bwd_d_barrier();
                 for (int i = tid; i < kDRounds * 32; i += CT) S.red[i] = 0.f;
             };
@@ -714,18 +714,14 @@ __device__ __forceinline__ void bwd_tc_phase0(const BwdArgs& a, unsigned char* s
 #pragma unroll
                         for (int i = 0; i < 32; ++i) {
                             const int vi = 32 * r + i;
-                            // w = 1: [a1 dA | m dA | dA];   w = 2: [a1 dA | a1 dB | m dA | m dB | dA dB]
+                            // w = 1: [a1 dA | m dA];   w = 2: [a1 dA | a1 dB | m dA | m dB]   (m = [y1 > 0]).  The constant-one
+                            // channel F has a1 = 1, so slot (q, F) of the a1 blocks IS the sd2 bias sum of dimension q.
                             const int q = vi / FPK, e = vi - q * FPK;
                             float val = 0.f;
-                            if (q < 4) {
+                            if (q < 2 * w) {
                                 const float yv = y1[e];
-                                const bool is_a = w == 1 ? (q == 0) : (q < 2);
-                                const bool use = w == 1 ? (q < 2) : true;
-                                const float dsel = w == 1 ? dA : ((q & 1) ? dB : dA);
-                                val = use ? (is_a ? fmaxf(yv, 0.f) * dsel : (yv > 0.f ? dsel : 0.f)) : 0.f;
-                                if (w == 1 && q == 2 && e == 0) val = dA;
-                            } else if (w == 2) {
-                                if (vi == 4 * FPK) val = dA; else if (vi == 4 * FPK + 1) val = dB;
+                                const float dsel = (w == 2 && (q & 1)) ? dB : dA;
+                                val = q < w ? fmaxf(yv, 0.f) * dsel : (yv > 0.f ? dsel : 0.f);
                             }
                             v[i] = val;
                         }
