@@ -113,12 +113,26 @@ class Flow_Mixture_Model(Local_Cond_RNVP_MC_Global_RNVP_VAE):
 
     def _base(self, g_sample):
         """Base Gaussian; the reference re-evaluates p_prior once per component (models.py:171 via
-        :163-166), which advances its BatchNorm running statistics K times per step -- kept."""
+        :163-166), which advances its BatchNorm running statistics K times per step with the same batch
+        statistics.  Kept, in closed form: K momentum updates with one batch statistic b are
+        r_K = (1-m)^K r_0 + (1 - (1-m)^K) b, and b follows from the single evaluation's own update."""
+        K = self.n_components
+        track = self.training and K > 1 and self.p_decoder_base_type in ('free', 'freevar')
+        bns = [m for m in self.p_prior.modules() if isinstance(m, nn.modules.batchnorm._BatchNorm)] if track else []
+        before = [(bn.running_mean.clone(), bn.running_var.clone()) for bn in bns]
         mu_b, lv_b = self.base_gaussian(g_sample)
-        if self.training and self.p_decoder_base_type in ('free', 'freevar'):
-            with torch.no_grad():
-                for _ in range(self.n_components - 1):
-                    self.p_prior(g_sample)
+        with torch.no_grad():
+            for bn, (rm0, rv0) in zip(bns, before):
+                m = bn.momentum
+                if m is None or not bn.track_running_stats:
+                    for _ in range(K - 1):          # cumulative-average BatchNorm: no closed form worth having
+                        self.p_prior(g_sample)
+                    break
+                keep = (1.0 - m) ** K
+                for r, r0 in ((bn.running_mean, rm0), (bn.running_var, rv0)):
+                    b = (r - (1.0 - m) * r0) / m
+                    r.copy_(keep * r0 + (1.0 - keep) * b)
+                bn.num_batches_tracked += K - 1
         return mu_b, lv_b
 
     def decode(self, p_input, g_sample, n_sampled_points, labeled_samples=False, warmup=False):

@@ -1,0 +1,73 @@
+"""The single-pass TF32 tier of the no-grad eval-mode NLL and of the sampling pass (gwtf_stack_desc.eval_precision =
+GWTF_PRECISION_TF32) against the fp64 reference results.  north_star: "any bf16 tensor-core path within a stated
+looser bound, validated against fp32".  Stated bounds (measured values are recorded in profiles/r02_precision.txt):
+
+  per-point NLL, |err| / max(|nll|, 1):   <= 2e-5 on the random-init C1 / C3 models (the operating point of the benches),
+                                          <= 1e-3 on the golden models whose last layers were scaled x25 away from init
+  samples, max |err| / max |x|:           <= 1e-3 (golden models)
+
+Training, and anything differentiated, always runs the fp32-grade 3xTF32 path: the tier does not apply there."""
+import pytest
+import torch
+
+from tests import parity
+from tests.util import GOLDEN_CASES, Golden, nll_err
+
+pytestmark = pytest.mark.gpu
+
+TIER_CASES = [c for c in GOLDEN_CASES if c != 'small_wide_learned']      # F = 44 runs on mma.sync: no TF32 tier there
+
+
+@pytest.fixture(autouse=True)
+def tf32_tier():
+    from go_with_the_flows_b200 import _native as nat
+    from go_with_the_flows_b200 import flowstack
+    pe = flowstack.set_default('engine', nat.ENGINE_TC)
+    pp = flowstack.set_default('eval_precision', nat.PRECISION_TF32)
+    yield
+    flowstack.set_default('engine', pe)
+    flowstack.set_default('eval_precision', pp)
+
+
+@pytest.mark.parametrize('case', TIER_CASES)
+def test_tf32_eval_nll_on_goldens(case):
+    gd = Golden(case)
+    err = parity.dropin_eval_fused_error(gd)
+    print('tf32 eval nll', case, err)
+    assert err < 1e-3
+
+
+@pytest.mark.parametrize('case', TIER_CASES)
+def test_tf32_sampling_on_goldens(case):
+    gd = Golden(case)
+    err, labels_ok = parity.dropin_sample_errors(gd)
+    print('tf32 sampling', case, err)
+    assert labels_ok                      # the component assignment does not depend on the tier
+    assert err < 1e-3
+
+
+@pytest.mark.parametrize('cfg_name', ['generative', 'autoencoding'])
+def test_tf32_eval_nll_full_size_random_init(cfg_name):
+    from tests.test_gpu_fullsize import _model, oracle_case
+    cfg, p, g, (want, _, _, _), _ = oracle_case(cfg_name, 4, 2048, False)
+    _, model = _model(cfg_name)
+    model = model.cuda().eval()
+    model.mode = 'training'
+    with torch.no_grad():
+        out, _ = model.decode(p.cuda(), g.cuda(), 2048)
+    err = nll_err(out[0]['mixture_nll'].cpu(), want['nll'].detach())
+    print('tf32 eval nll full size', cfg_name, err)
+    assert err < 2e-5
+
+
+def test_training_ignores_the_tier():
+    """Gradients need the fp32-grade path: a train-mode (or grad-enabled) pass keeps its fp32-grade accuracy under both
+    settings (floating-point atomics make two runs differ in the last bits, so the check is on the error level)."""
+    from go_with_the_flows_b200 import _native as nat
+    from go_with_the_flows_b200 import flowstack
+    gd = Golden('small_free_learned')
+    res_tf32 = parity.dropin_nll_errors(gd, 'train', fused_nll=True)
+    flowstack.set_default('eval_precision', nat.PRECISION_3XTF32)
+    res_3x = parity.dropin_nll_errors(gd, 'train', fused_nll=True)
+    assert res_tf32['nll'] < 2e-5 and res_3x['nll'] < 2e-5
+    assert res_tf32['dparams'] < 2e-5 and res_3x['dparams'] < 2e-5
