@@ -523,6 +523,10 @@ def main():
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    # stdout carries exactly ONE line, the JSON: anything a library prints there (NCCL's version banner ...) goes to stderr
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     if not torch.cuda.is_available():
         raise SystemExit('bench.py needs a CUDA device (there is no CPU fallback for the flow kernels)')
     torch.cuda.set_device(local_rank)
@@ -657,7 +661,7 @@ def main():
             line['cpu_baseline'] = {'value': cb * cn / sec, 'unit': 'points/s', 'cores': cores, 'kind': kind,
                                     'sample': 'same model, train-mode fwd+bwd, %d clouds x %d points, 2 timed steps '
                                               'after 1 warm-up (%.2f s/step)' % (cb, cn, sec)}
-        print(json.dumps(line), flush=True)
+        os.write(json_fd, (json.dumps(line) + '\n').encode())
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -131,7 +131,9 @@ class Flow_Mixture_Model(Local_Cond_RNVP_MC_Global_RNVP_VAE):
                 keep = (1.0 - m) ** K
                 for r, r0 in ((bn.running_mean, rm0), (bn.running_var, rv0)):
                     b = (r - (1.0 - m) * r0) / m
-                    r.copy_(keep * r0 + (1.0 - keep) * b)
+                    # (.data: batch_norm's backward holds the buffer; its own in-kernel update does not bump the
+                    # version counter either)
+                    r.data.copy_(keep * r0 + (1.0 - keep) * b)
                 bn.num_batches_tracked += K - 1
         return mu_b, lv_b
 

@@ -2,9 +2,12 @@
 GWTF_PRECISION_TF32) against the fp64 reference results.  north_star: "any bf16 tensor-core path within a stated
 looser bound, validated against fp32".  Stated bounds (measured values are recorded in profiles/r02_precision.txt):
 
-  per-point NLL, |err| / max(|nll|, 1):   <= 2e-5 on the random-init C1 / C3 models (the operating point of the benches),
-                                          <= 1e-3 on the golden models whose last layers were scaled x25 away from init
-  samples, max |err| / max |x|:           <= 1e-3 (golden models)
+  per-point NLL, |err| / max(|nll|, 1):   <= 1e-5 on the random-init C1 / C3 models (the operating point of the benches;
+                                          measured 5e-7 / 8e-7),
+                                          <= 1e-2 on the golden models, whose last layers were scaled x25 away from
+                                          init (measured 1.6e-4 .. 4e-4; 4e-3 on the ill-conditioned 'fixed'-base case,
+                                          where the fp32 CPU oracle itself sits at 5e-5)
+  samples, max |err| / max |x|:           <= 1e-3 on the golden models (measured 1.7e-4 .. 2.9e-4)
 
 Training, and anything differentiated, always runs the fp32-grade 3xTF32 path: the tier does not apply there."""
 import pytest
@@ -34,7 +37,7 @@ def test_tf32_eval_nll_on_goldens(case):
     gd = Golden(case)
     err = parity.dropin_eval_fused_error(gd)
     print('tf32 eval nll', case, err)
-    assert err < 1e-3
+    assert err < 1e-2
 
 
 @pytest.mark.parametrize('case', TIER_CASES)
@@ -57,7 +60,7 @@ def test_tf32_eval_nll_full_size_random_init(cfg_name):
         out, _ = model.decode(p.cuda(), g.cuda(), 2048)
     err = nll_err(out[0]['mixture_nll'].cpu(), want['nll'].detach())
     print('tf32 eval nll full size', cfg_name, err)
-    assert err < 2e-5
+    assert err < 1e-5
 
 
 def test_training_ignores_the_tier():
