@@ -181,7 +181,7 @@ __device__ __forceinline__ void bwd_tc_phase1(const BwdArgs& a, unsigned char* s
             if (elect_one()) {
                 int tiles_s = 0;
                 {
-                    RoundIter it(t_begin, t_end, tps, nullptr, B);
+                    RoundIter it(t_begin, t_end, tps, nullptr, B, kBSlots);
                     int base, count, b;
                     while (it.next(base, count, b)) tiles_s += (s < count) ? 1 : 0;
                 }
@@ -198,12 +198,12 @@ __device__ __forceinline__ void bwd_tc_phase1(const BwdArgs& a, unsigned char* s
                     issue_ts<FPK, FPN>(ts + C::D, ts + C::Ahi, ts + C::Alo, S.B1.hi, S.B1.lo);
                     tc_commit(&S.done[s]);
                     mbar_wait(&S.req[s], req_phase); req_phase ^= 1u; tc_fence_after();
-                    issue_ts<FPK, FPN>(ts + C::D, ts + C::Ahi, ts + C::Alo, S.W1T.hi, S.W1T.lo);
+                    issue_ts<FPK, FPN>(ts + C::Ahi, ts + C::D, ts + C::P, S.W1T.hi, S.W1T.lo);     // r lives in D | P
                     tc_commit(&S.done[s]);
                     issue_point_contraction<FPK>(tg, mn, mn + kMnFloats, mn + 2 * kMnFloats, mn + 3 * kMnFloats);
                     tc_commit(&S.buf_free);
                     mbar_wait(&S.req[s], req_phase); req_phase ^= 1u; tc_fence_after();
-                    issue_ts<FPK, 16>(ts + C::D, ts + C::Ahi, ts + C::Alo, S.Q0.hi, S.Q0.lo);
+                    issue_ts<FPK, 16>(ts + C::Ahi, ts + C::D, ts + C::P, S.Q0.hi, S.Q0.lo);        // dy0 lives in D | P
                     tc_commit(&S.done[s]);
                 }
                 // drain: everything this thread issued (its dW1 chain included) has completed
@@ -220,7 +220,7 @@ __device__ __forceinline__ void bwd_tc_phase1(const BwdArgs& a, unsigned char* s
             // parities continue across the net loop: count what this slot did in the previous net
             int tiles_s = 0;
             {
-                RoundIter it0(t_begin, t_end, tps, nullptr, B);
+                RoundIter it0(t_begin, t_end, tps, nullptr, B, kBSlots);
                 int base, count, b;
                 while (it0.next(base, count, b)) tiles_s += (slot < count) ? 1 : 0;
             }
@@ -230,7 +230,7 @@ __device__ __forceinline__ void bwd_tc_phase1(const BwdArgs& a, unsigned char* s
             float sacc[4] = {0.f, 0.f, 0.f, 0.f};
             int cur_b = -1;
             int seq = net * my_tiles;              // sequence number of this CTA's point contractions (buffer turns)
-            RoundIter it(t_begin, t_end, tps, nullptr, B);
+            RoundIter it(t_begin, t_end, tps, nullptr, B, kBSlots);
             int base, count, b;
             while (it.next(base, count, b)) {
                 if (b != cur_b) {
@@ -316,16 +316,14 @@ __device__ __forceinline__ void bwd_tc_phase1(const BwdArgs& a, unsigned char* s
                 }
                 tmem_wait_st();
                 request();                                              // -> batch B: y1
-                // our turn on the point-contraction operands: contraction number my_seq - 1 has been consumed
-                if (my_seq > 0) mbar_wait(&S.buf_free, (uint32_t)((my_seq - 1) & 1));
                 wait_done();
+                // r = dh1, written over the y1 / P columns it was computed from (hi -> D, lo -> P): the a0 operand stays
+                // intact for the point contraction, and nothing here needs the shared operand buffer yet
 #pragma unroll
                 for (int c = 0; c < FPK; c += 8) {
-                    float y1[8], p8[8], ah[8], al[8], rh[8], rl[8];
+                    float y1[8], p8[8], rh[8], rl[8];
                     tmem_ld8(trow + C::D + c, y1);
                     tmem_ld8(trow + C::P + c, p8);
-                    tmem_ld8(trow + C::Ahi + c, ah);
-                    tmem_ld8(trow + C::Alo + c, al);
                     tmem_wait_ld();
 #pragma unroll
                     for (int i = 0; i < 8; i += 2) {
@@ -336,14 +334,27 @@ __device__ __forceinline__ void bwd_tc_phase1(const BwdArgs& a, unsigned char* s
                         split_tf32(r0, rh[i], rl[i]);
                         split_tf32(r1, rh[i + 1], rl[i + 1]);
                     }
-                    tmem_st8(trow + C::Ahi + c, rh);
-                    tmem_st8(trow + C::Alo + c, rl);
+                    tmem_st8(trow + C::D + c, rh);
+                    tmem_st8(trow + C::P + c, rl);
+                }
+                tmem_wait_st();
+                // our turn on the point-contraction operands (contraction number my_seq - 1 has been consumed); the turn
+                // only covers the copy TMEM -> shared memory and the MMA chain that reads it
+                if (my_seq > 0) mbar_wait(&S.buf_free, (uint32_t)((my_seq - 1) & 1));
+#pragma unroll
+                for (int c = 0; c < FPK; c += 8) {
+                    float rh[8], rl[8], ah[8], al[8];
+                    tmem_ld8(trow + C::D + c, rh);
+                    tmem_ld8(trow + C::P + c, rl);
+                    tmem_ld8(trow + C::Ahi + c, ah);
+                    tmem_ld8(trow + C::Alo + c, al);
+                    tmem_wait_ld();
                     store_mn_chunk(mn, c >> 3, wtid, rh);
                     store_mn_chunk(mn + kMnFloats, c >> 3, wtid, rl);
                     store_mn_chunk(mn + 2 * kMnFloats, c >> 3, wtid, ah);
                     store_mn_chunk(mn + 3 * kMnFloats, c >> 3, wtid, al);
                 }
-                tmem_wait_st();
+                tc_fence_before();
                 fence_proxy_async();
                 request();                                              // -> batch C: da0, then dW1 += r^T a0
                 wait_done();                                            // (da0 only: dW1 keeps running)
@@ -356,7 +367,7 @@ __device__ __forceinline__ void bwd_tc_phase1(const BwdArgs& a, unsigned char* s
 #pragma unroll
                     for (int c = 0; c < FPK; c += 8) {
                         float d8[8], hi[8], lo[8];
-                        tmem_ld8(trow + C::D + c, d8);
+                        tmem_ld8(trow + C::Ahi + c, d8);
                         tmem_wait_ld();
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
@@ -364,8 +375,8 @@ __device__ __forceinline__ void bwd_tc_phase1(const BwdArgs& a, unsigned char* s
                             dy[c + i] = pos ? d8[i] : 0.f;
                             split_tf32(dy[c + i], hi[i], lo[i]);
                         }
-                        tmem_st8(trow + C::Ahi + c, hi);
-                        tmem_st8(trow + C::Alo + c, lo);
+                        tmem_st8(trow + C::D + c, hi);
+                        tmem_st8(trow + C::P + c, lo);
                     }
                     tmem_wait_st();
                     request();                                          // -> batch D: du
@@ -384,7 +395,7 @@ __device__ __forceinline__ void bwd_tc_phase1(const BwdArgs& a, unsigned char* s
                 wait_done();
                 {
                     float du[8];
-                    tmem_ld8(trow + C::D, du);
+                    tmem_ld8(trow + C::Ahi, du);
                     tmem_wait_ld();
                     if (valid) {
 #pragma unroll
@@ -441,7 +452,7 @@ __device__ __forceinline__ void bwd_tc_phase1(const BwdArgs& a, unsigned char* s
 //     dW2 = sum dO a1;   dt = sum_d W2_d sum dO_d [y1>0];   ds = (sum_d W2_d sum dO_d a1 - t dt) / s     (a1 = [y1>0] y1)
 //   so the CUDA cores never form da1 = W2^T dO per point and never touch a per-channel constant in the tile loop.
 // =============================================================================================
-constexpr int kDSlots = 3;
+constexpr int kDSlots = 4;
 constexpr int kBwdDThreads = kDSlots * 128 + kDSlots * 32;
 constexpr int kDRounds = 5;                                     // reduce-scatter rounds of 32 values (<= 4 FPK values)
 
@@ -542,7 +553,7 @@ __device__ __forceinline__ void bwd_tc_phase0(const BwdArgs& a, unsigned char* s
         // how many requests each slot made in the first pass (3 per tile + drain): barrier parities go on from there
         auto tiles_of = [&](int s) {
             int n = 0;
-            RoundIter it0(t_begin, t_end, tps, nullptr, B);
+            RoundIter it0(t_begin, t_end, tps, nullptr, B, kDSlots);
             int base, count, b;
             while (it0.next(base, count, b)) n += (s < count) ? 1 : 0;
             return n;
@@ -618,7 +629,7 @@ __device__ __forceinline__ void bwd_tc_phase0(const BwdArgs& a, unsigned char* s
             };
 
             int cur_b = -1;
-            RoundIter it(t_begin, t_end, tps, nullptr, B);
+            RoundIter it(t_begin, t_end, tps, nullptr, B, kDSlots);
             int base, count, b;
             while (it.next(base, count, b)) {
                 if (b != cur_b) {

@@ -46,13 +46,14 @@ struct TcPersistSmem {
     double dred[16];
 };
 
-// the CTA's contiguous tile range cut into rounds of <= kSlots tiles that never straddle a shape.  Dense mode:
+// the CTA's contiguous tile range cut into rounds of <= `slots` tiles that never straddle a shape.  Dense mode:
 // every shape has `tps` tiles; segmented mode: shape b of this component owns tiles [pre[b], pre[b+1]).
 struct RoundIter {
     int t, t_end, tps;
     const int32_t* pre;          // null = dense
-    int b, s_begin, s_end;
-    __device__ __forceinline__ RoundIter(int t0, int t1, int tps_, const int32_t* pre_, int B) : t(t0), t_end(t1), tps(tps_), pre(pre_) {
+    int b, s_begin, s_end, slots;
+    __device__ __forceinline__ RoundIter(int t0, int t1, int tps_, const int32_t* pre_, int B, int slots_ = kSlots)
+        : t(t0), t_end(t1), tps(tps_), pre(pre_), slots(slots_) {
         if (!pre) { b = t0 / tps; s_begin = b * tps; s_end = s_begin + tps; return; }
         int lo = 0, hi = B;                  // largest b with pre[b] <= t0
         while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (pre[mid] <= t0) lo = mid; else hi = mid; }
@@ -62,7 +63,7 @@ struct RoundIter {
         if (t >= t_end) return false;
         while (t >= s_end) { ++b; s_begin = s_end; s_end = pre ? pre[b + 1] : s_end + tps; }
         const int ti = t - s_begin;
-        int end = s_begin + min(s_end - s_begin, (ti / kSlots + 1) * kSlots);
+        int end = s_begin + min(s_end - s_begin, (ti / slots + 1) * slots);
         end = min(end, t_end);
         base = t;
         count = end - t;
