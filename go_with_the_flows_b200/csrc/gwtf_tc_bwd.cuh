@@ -25,7 +25,14 @@ namespace gwtf {
 
 constexpr int kBSlots = 2;
 constexpr int kBwdThreads = kBSlots * 128 + kBSlots * 32;      // compute warpgroups + one issuer warp per slot
-constexpr int kMnFloats = 2 * (128 / 4) * 128;                 // one MN-major operand: 2 atoms of 32 channels x 128 points
+// Point-contraction operands (MN-major, 128B swizzle / 32B base): an mn-atom is 32 channels x 128 points = 16 KB.  Each of
+// the four arrays (r_hi, r_lo, a0_hi, a0_lo) owns ONE atom (channels 0..31); channels 32..39 of array `a` live in 32-byte
+// slot `a` of every 128-byte row of a fifth, shared atom, which each array's descriptor reaches through its own
+// leading-dimension offset (tools/tc_probe5.cu): 80 KB instead of 128 KB.  Rows 40..63 of the M = 64 operand read
+// whatever the neighbouring slots hold -- they only feed accumulator rows nobody reads.
+constexpr int kMnAtom = (128 / 4) * 128;                       // floats per atom
+constexpr int kMnFloats = kMnAtom;                             // stride between the four arrays
+constexpr int kMnTotal = 5 * kMnAtom + 64;                     // + the shared atom + slack for reads past its end
 
 __device__ __forceinline__ void bwd_compute_barrier() { asm volatile("bar.sync 2, %0;" ::"n"(kBSlots * 128) : "memory"); }
 __device__ __forceinline__ void wg_barrier(int slot) { asm volatile("bar.sync %0, 128;" ::"r"(3 + slot) : "memory"); }
@@ -49,17 +56,22 @@ struct TcBwdESmem {
     float xd_hi[kBSlots][128 * 8], xd_lo[kBSlots][128 * 8];
     float2 bg[FPN];                // (beta, gamma) of the current shape
     float red[4 * 32];
+    alignas(16) float col[kBSlots * 4][kColTile];
     uint64_t bar_tma, req[kBSlots], done[kBSlots], buf_free;
     uint32_t tmem_base;
 };
 
 // D[M=64 x N] (+)= A^T B over the 128 points of a tile, both operands MN-major (sw32) in shared memory, 3xTF32
+__device__ __forceinline__ uint64_t mn_operand_desc(const float* mn, int arr) {
+    const float* base = mn + arr * kMnFloats;
+    const uint32_t lbo = smem_u32(mn + 4 * kMnFloats + 8 * arr) - smem_u32(base);      // -> slot `arr` of the shared atom
+    return make_smem_desc(base, lbo, 512u, 1u);
+}
 template <int N>
-__device__ __forceinline__ void issue_point_contraction(uint32_t d_tmem, const float* a_hi, const float* a_lo,
-                                                        const float* b_hi, const float* b_lo) {
+__device__ __forceinline__ void issue_point_contraction(uint32_t d_tmem, const float* mn) {
     const uint32_t idesc = make_idesc_tf32(64, N, 1, 1);
-    const uint64_t ah = make_smem_desc_mnmajor_sw32(a_hi, 128), al = make_smem_desc_mnmajor_sw32(a_lo, 128);
-    const uint64_t bh = make_smem_desc_mnmajor_sw32(b_hi, 128), bl = make_smem_desc_mnmajor_sw32(b_lo, 128);
+    const uint64_t ah = mn_operand_desc(mn, 0), al = mn_operand_desc(mn, 1);
+    const uint64_t bh = mn_operand_desc(mn, 2), bl = mn_operand_desc(mn, 3);
 #pragma unroll
     for (int pass = 0; pass < 3; ++pass) {
         const uint64_t a = pass == 1 ? al : ah;
@@ -71,8 +83,9 @@ __device__ __forceinline__ void issue_point_contraction(uint32_t d_tmem, const f
 }
 
 // this thread's 8 channels (one 32-byte chunk) of point `p` into an MN-major operand
-__device__ __forceinline__ void store_mn_chunk(float* arr, int chunk, int p, const float (&v)[8]) {
-    float* dst = arr + mnmajor_sw32_offset(8 * chunk, p, 128);
+__device__ __forceinline__ void store_mn_chunk(float* mn, int arr, int chunk, int p, const float (&v)[8]) {
+    float* dst = chunk < 4 ? mn + arr * kMnFloats + mnmajor_sw32_offset(8 * chunk, p, 128)
+                           : mn + 4 * kMnFloats + (p >> 2) * 128 + (p & 3) * 32 + ((arr ^ (p & 3)) << 3);
     *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
     *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
 }
@@ -139,7 +152,6 @@ __device__ __forceinline__ void bwd_tc_phase1(const BwdArgs& a, unsigned char* s
     const int per_cta = (total_tiles + gridDim.x - 1) / gridDim.x;
     const int t_begin = min(blockIdx.x * per_cta, total_tiles), t_end = min(t_begin + per_cta, total_tiles);
     const int my_tiles = t_end - t_begin;
-    const int rounds_n = (k + 1) * FPK <= 96 ? ((k + 1) * FPK <= 64 ? 2 : 3) : 4;    // reduce-scatter rounds of 32 values
 
 #pragma unroll 1
     for (int net = 0; net < 2; ++net) {
@@ -200,7 +212,7 @@ __device__ __forceinline__ void bwd_tc_phase1(const BwdArgs& a, unsigned char* s
                     mbar_wait(&S.req[s], req_phase); req_phase ^= 1u; tc_fence_after();
                     issue_ts<FPK, FPN>(ts + C::Ahi, ts + C::D, ts + C::P, S.W1T.hi, S.W1T.lo);     // r lives in D | P
                     tc_commit(&S.done[s]);
-                    issue_point_contraction<FPK>(tg, mn, mn + kMnFloats, mn + 2 * kMnFloats, mn + 3 * kMnFloats);
+                    issue_point_contraction<FPK>(tg, mn);
                     tc_commit(&S.buf_free);
                     mbar_wait(&S.req[s], req_phase); req_phase ^= 1u; tc_fence_after();
                     issue_ts<FPK, 16>(ts + C::Ahi, ts + C::D, ts + C::P, S.Q0.hi, S.Q0.lo);        // dy0 lives in D | P
@@ -227,7 +239,9 @@ __device__ __forceinline__ void bwd_tc_phase1(const BwdArgs& a, unsigned char* s
             uint32_t done_phase = (uint32_t)((net * tiles_s * 4 + net) & 1);
             auto request = [&]() { tc_fence_before(); mbar_arrive(req); };
             auto wait_done = [&]() { mbar_wait(done, done_phase); done_phase ^= 1u; tc_fence_after(); };
-            float sacc[4] = {0.f, 0.f, 0.f, 0.f};
+            // column sums of dy0 (1 | xa | xb): acc0 = channel `lane`, acc1 = channel 32 + (lane & 7)
+            float acc0[3] = {0.f, 0.f, 0.f}, acc1[3] = {0.f, 0.f, 0.f};
+            float* coltile = S.col[warp];
             int cur_b = -1;
             int seq = net * my_tiles;              // sequence number of this CTA's point contractions (buffer turns)
             RoundIter it(t_begin, t_end, tps, nullptr, B, kBSlots);
@@ -349,21 +363,21 @@ __device__ __forceinline__ void bwd_tc_phase1(const BwdArgs& a, unsigned char* s
                     tmem_ld8(trow + C::Ahi + c, ah);
                     tmem_ld8(trow + C::Alo + c, al);
                     tmem_wait_ld();
-                    store_mn_chunk(mn, c >> 3, wtid, rh);
-                    store_mn_chunk(mn + kMnFloats, c >> 3, wtid, rl);
-                    store_mn_chunk(mn + 2 * kMnFloats, c >> 3, wtid, ah);
-                    store_mn_chunk(mn + 3 * kMnFloats, c >> 3, wtid, al);
+                    store_mn_chunk(mn, 0, c >> 3, wtid, rh);
+                    store_mn_chunk(mn, 1, c >> 3, wtid, rl);
+                    store_mn_chunk(mn, 2, c >> 3, wtid, ah);
+                    store_mn_chunk(mn, 3, c >> 3, wtid, al);
                 }
                 tc_fence_before();
                 fence_proxy_async();
                 request();                                              // -> batch C: da0, then dW1 += r^T a0
                 wait_done();                                            // (da0 only: dW1 keeps running)
                 {
-                    float v[32];
                     const float xa = keepd[0] == 0 ? x[0] : (keepd[0] == 1 ? x[1] : x[2]);
-                    const float xb = keepd[1] == 0 ? x[0] : (keepd[1] == 1 ? x[1] : x[2]);
-                    // dy0 = [y0 > 0] da0 -> operand; values (dy0 | dy0 xa | dy0 xb) reduced over the warp's 32 points
-                    float dy[FPK];
+                    const float xb = k == 2 ? (keepd[1] == 0 ? x[0] : (keepd[1] == 1 ? x[1] : x[2])) : 0.f;
+                    // dy0 = [y0 > 0] da0 -> operand (hi -> D, lo -> P) and, raw, into row `lane` of the warp's column tile
+                    __syncwarp();
+                    float4* crow = reinterpret_cast<float4*>(coltile + lane * kColPitch);
 #pragma unroll
                     for (int c = 0; c < FPK; c += 8) {
                         float d8[8], hi[8], lo[8];
@@ -372,24 +386,43 @@ __device__ __forceinline__ void bwd_tc_phase1(const BwdArgs& a, unsigned char* s
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
                             const bool pos = (c + i < 32) ? ((m0lo >> (c + i)) & 1u) : ((m0hi >> (c + i - 32)) & 1u);
-                            dy[c + i] = pos ? d8[i] : 0.f;
-                            split_tf32(dy[c + i], hi[i], lo[i]);
+                            d8[i] = pos ? d8[i] : 0.f;
+                            split_tf32(d8[i], hi[i], lo[i]);
                         }
                         tmem_st8(trow + C::D + c, hi);
                         tmem_st8(trow + C::P + c, lo);
+                        crow[c / 4] = make_float4(d8[0], d8[1], d8[2], d8[3]);
+                        crow[c / 4 + 1] = make_float4(d8[4], d8[5], d8[6], d8[7]);
                     }
+                    *reinterpret_cast<float2*>(coltile + 32 * kColPitch + 2 * lane) = make_float2(xa, xb);
                     tmem_wait_st();
                     request();                                          // -> batch D: du
+                    // sums of dy0 (1 | xa | xb) over the warp's 32 points: lane L sums column L
+                    __syncwarp();
+                    const float* wts = coltile + 32 * kColPitch;
+#pragma unroll 8
+                    for (int pp = 0; pp < 32; ++pp) {
+                        const float v = lane < FPK ? coltile[pp * kColPitch + lane] : 0.f;
+                        const float2 x2 = *reinterpret_cast<const float2*>(wts + 2 * pp);
+                        acc0[0] += v;
+                        acc0[1] = fmaf(v, x2.x, acc0[1]);
+                        acc0[2] = fmaf(v, x2.y, acc0[2]);
+                    }
+                    if (FPK > 32) {
+                        float t0 = 0.f, t1 = 0.f, t2 = 0.f;
+                        const int ch = 32 + (lane & 7), p0 = (lane >> 3) * 8;
 #pragma unroll
-                    for (int r = 0; r < 4; ++r) {
-                        if (r < rounds_n) {
-#pragma unroll
-                            for (int i = 0; i < 32; ++i) {
-                                const int vi = 32 * r + i, wsel = vi / FPK, e = vi - wsel * FPK;
-                                v[i] = wsel == 0 ? dy[e] : (wsel == 1 ? dy[e] * xa : (wsel == 2 ? dy[e] * xb : 0.f));
-                            }
-                            sacc[r] += warp_reduce_scatter32(v, lane);
+                        for (int pp = 0; pp < 8; ++pp) {
+                            const float v = ch < FPK ? coltile[(p0 + pp) * kColPitch + ch] : 0.f;
+                            const float2 x2 = *reinterpret_cast<const float2*>(wts + 2 * (p0 + pp));
+                            t0 += v;
+                            t1 = fmaf(v, x2.x, t1);
+                            t2 = fmaf(v, x2.y, t2);
                         }
+                        t0 += __shfl_xor_sync(0xffffffffu, t0, 8);  t0 += __shfl_xor_sync(0xffffffffu, t0, 16);
+                        t1 += __shfl_xor_sync(0xffffffffu, t1, 8);  t1 += __shfl_xor_sync(0xffffffffu, t1, 16);
+                        t2 += __shfl_xor_sync(0xffffffffu, t2, 8);  t2 += __shfl_xor_sync(0xffffffffu, t2, 16);
+                        acc1[0] += t0; acc1[1] += t1; acc1[2] += t2;
                     }
                 }
                 wait_done();
@@ -407,8 +440,10 @@ __device__ __forceinline__ void bwd_tc_phase1(const BwdArgs& a, unsigned char* s
             request();
             wait_done();
 #pragma unroll
-            for (int r = 0; r < 4; ++r)
-                if (r < rounds_n) atomicAdd(&S.red[32 * r + lane], sacc[r]);
+            for (int q = 0; q < 3; ++q) {
+                if (lane < FPK) atomicAdd(&S.red[q * FPK + lane], acc0[q]);
+                if (lane < 8 && 32 + lane < FPK) atomicAdd(&S.red[q * FPK + 32 + lane], acc1[q]);
+            }
         }
         __syncthreads();
         // ---- flush the per-channel sums of this net: dbeta0 = S1, dW0 raw sums, dgamma0 = r0 . (Sx, S1)
@@ -454,7 +489,6 @@ __device__ __forceinline__ void bwd_tc_phase1(const BwdArgs& a, unsigned char* s
 // =============================================================================================
 constexpr int kDSlots = 4;
 constexpr int kBwdDThreads = kDSlots * 128 + kDSlots * 32;
-constexpr int kDRounds = 5;                                     // reduce-scatter rounds of 32 values (<= 4 FPK values)
 
 __device__ __forceinline__ void bwd_d_barrier() { asm volatile("bar.sync 2, %0;" ::"n"(kDSlots * 128) : "memory"); }
 
@@ -465,7 +499,8 @@ struct TcBwdDSmem {
     TcLayerOps<FPK, FPN> ops;      // B0 | B1 (folded, per shape) | B2 of the current net
     float x_hi[kDSlots][128 * 8], x_lo[kDSlots][128 * 8];
     float corr[12];
-    float red[kDRounds * 32];
+    float red[4 * FPK];             // [a1 dA | a1 dB | m dA | m dB] per channel (m = [y1 > 0])
+    alignas(16) float col[kDSlots * 4][kColTile];
     uint64_t bar_tma, req[kDSlots], done[kDSlots];
     uint32_t tmem_base;
 };
@@ -526,8 +561,6 @@ __device__ __forceinline__ void bwd_tc_phase0(const BwdArgs& a, unsigned char* s
     int wd[2];                                                   // first / second warped dimension
     wd[0] = (wm & 1u) ? 0 : ((wm & 2u) ? 1 : 2);
     wd[1] = w == 2 ? ((wm & 4u) ? 2 : 1) : wd[0];
-    const int n_vals = 2 * w * FPK;                              // (a1 dO_d | [y1>0] dO_d) per channel and warped dim
-    const int rounds_n = (n_vals + 31) / 32;
     float* dpr = a.dparams + (size_t)(j * L + l) * a.d.rec_stride;
     double* bs = a.bsum + (size_t)j * 8 * F;
     const uint32_t tbase = S.tmem_base;
@@ -544,7 +577,7 @@ __device__ __forceinline__ void bwd_tc_phase0(const BwdArgs& a, unsigned char* s
         __syncthreads();
         stage_b0<FPK, FPN>(S.ops, S.W.q0[net], F, tid, kBwdDThreads);
         stage_b2<FPK, FPN>(S.ops, S.W.w2[net], S.W.b2[net], F, tid, kBwdDThreads);
-        for (int i = tid; i < kDRounds * 32; i += kBwdDThreads) S.red[i] = 0.f;
+        for (int i = tid; i < 4 * FPK; i += kBwdDThreads) S.red[i] = 0.f;
         fence_proxy_async();
         tc_fence_before();
         __syncthreads();
@@ -590,16 +623,17 @@ __device__ __forceinline__ void bwd_tc_phase0(const BwdArgs& a, unsigned char* s
             uint32_t done_phase = pass == 0 ? 0u : (uint32_t)((tiles_of(slot) * 3 + 1) & 1);
             auto request = [&]() { tc_fence_before(); mbar_arrive(req); };
             auto wait_done = [&]() { mbar_wait(done, done_phase); done_phase ^= 1u; tc_fence_after(); };
-            float sacc[kDRounds];
-#pragma unroll
-            for (int r = 0; r < kDRounds; ++r) sacc[r] = 0.f;
+            // column sums of this warp's points: acc0 = channel `lane`, acc1 = channel 32 + (lane & 7)
+            float acc0[4] = {0.f, 0.f, 0.f, 0.f}, acc1[4] = {0.f, 0.f, 0.f, 0.f};      // a1 dA | a1 dB | m dA | m dB
+            float* coltile = S.col[warp];
 
             auto flush_shape = [&](int b) {
                 // per-shape sums -> block partials -> FiLM / sd2 gradients and the sd1_bn backward sums
 #pragma unroll
-                for (int r = 0; r < kDRounds; ++r) {
-                    if (r < rounds_n) atomicAdd(&S.red[32 * r + lane], sacc[r]);
-                    sacc[r] = 0.f;
+                for (int q = 0; q < 4; ++q) {
+                    if (lane < FPK) atomicAdd(&S.red[q * FPK + lane], acc0[q]);
+                    if (lane < 8 && 32 + lane < FPK) atomicAdd(&S.red[q * FPK + 32 + lane], acc1[q]);
+                    acc0[q] = 0.f; acc1[q] = 0.f;
                 }
                 bwd_d_barrier();
                 float* dfl = a.dfilm + ((size_t)(b * K + j) * L + l) * 4 * F;
@@ -610,7 +644,7 @@ __device__ __forceinline__ void bwd_tc_phase0(const BwdArgs& a, unsigned char* s
                     float Asum = 0.f, dt = 0.f;
                     for (int q = 0; q < w; ++q) {
                         const float wq = wd[q] == 0 ? w2.x : (wd[q] == 1 ? w2.y : w2.z);
-                        const float sa = S.red[q * FPK + f], sm = S.red[(w + q) * FPK + f];
+                        const float sa = S.red[q * FPK + f], sm = S.red[(2 + q) * FPK + f];
                         Asum = fmaf(wq, sa, Asum);
                         dt = fmaf(wq, sm, dt);
                         atomicAdd(&dpr[net * o.stride + o.W2 + q * F + f], sa);
@@ -625,7 +659,7 @@ __device__ __forceinline__ void bwd_tc_phase0(const BwdArgs& a, unsigned char* s
                 }
                 if (tid < w) atomicAdd(&dpr[net * o.stride + o.b2 + tid], S.red[tid * FPK + F]);
                 bwd_d_barrier();
-                for (int i = tid; i < kDRounds * 32; i += CT) S.red[i] = 0.f;
+                for (int i = tid; i < 4 * FPK; i += CT) S.red[i] = 0.f;
             };
 
             int cur_b = -1;
@@ -715,28 +749,41 @@ __device__ __forceinline__ void bwd_tc_phase0(const BwdArgs& a, unsigned char* s
                         dO[d] = dov;
                     }
                 }
-                // ---- sums over the warp's 32 points
+                // ---- sums over the warp's 32 points: rows of a1 into the warp's tile, columns summed by the reader lanes.
+                // The constant-one channel F has a1 = 1, so its a1 dA / a1 dB sums ARE the sd2 bias gradients.
                 const float dA = wd[0] == 0 ? dO[0] : (wd[0] == 1 ? dO[1] : dO[2]);
-                const float dB = wd[1] == 0 ? dO[0] : (wd[1] == 1 ? dO[1] : dO[2]);
+                const float dB = w == 2 ? (wd[1] == 0 ? dO[0] : (wd[1] == 1 ? dO[1] : dO[2])) : 0.f;
 #pragma unroll
-                for (int r = 0; r < kDRounds; ++r) {
-                    if (r < rounds_n) {
-                        float v[32];
+                for (int e = 0; e < FPK; ++e) y1[e] = fmaxf(y1[e], 0.f);
+                __syncwarp();                                           // the previous tile's readers are done
+                col_write_row<FPK>(coltile, lane, y1, dA, dB);
+                __syncwarp();
+                {
+                    const float* wts = coltile + 32 * kColPitch;
+#pragma unroll 8
+                    for (int pp = 0; pp < 32; ++pp) {
+                        const float v = lane < FPK ? coltile[pp * kColPitch + lane] : 0.f;
+                        const float2 d2 = *reinterpret_cast<const float2*>(wts + 2 * pp);
+                        acc0[0] = fmaf(v, d2.x, acc0[0]);
+                        acc0[1] = fmaf(v, d2.y, acc0[1]);
+                        if (v > 0.f) { acc0[2] += d2.x; acc0[3] += d2.y; }
+                    }
+                    if (FPK > 32) {
+                        float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
+                        const int ch = 32 + (lane & 7), p0 = (lane >> 3) * 8;
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) {
-                            const int vi = 32 * r + i;
-                            // w = 1: [a1 dA | m dA];   w = 2: [a1 dA | a1 dB | m dA | m dB]   (m = [y1 > 0]).  The constant-one
-                            // channel F has a1 = 1, so slot (q, F) of the a1 blocks IS the sd2 bias sum of dimension q.
-                            const int q = vi / FPK, e = vi - q * FPK;
-                            float val = 0.f;
-                            if (q < 2 * w) {
-                                const float yv = y1[e];
-                                const float dsel = (w == 2 && (q & 1)) ? dB : dA;
-                                val = q < w ? fmaxf(yv, 0.f) * dsel : (yv > 0.f ? dsel : 0.f);
-                            }
-                            v[i] = val;
+                        for (int pp = 0; pp < 8; ++pp) {
+                            const float v = ch < FPK ? coltile[(p0 + pp) * kColPitch + ch] : 0.f;
+                            const float2 d2 = *reinterpret_cast<const float2*>(wts + 2 * (p0 + pp));
+                            t0 = fmaf(v, d2.x, t0);
+                            t1 = fmaf(v, d2.y, t1);
+                            if (v > 0.f) { t2 += d2.x; t3 += d2.y; }
                         }
-                        sacc[r] += warp_reduce_scatter32(v, lane);
+                        t0 += __shfl_xor_sync(0xffffffffu, t0, 8);  t0 += __shfl_xor_sync(0xffffffffu, t0, 16);
+                        t1 += __shfl_xor_sync(0xffffffffu, t1, 8);  t1 += __shfl_xor_sync(0xffffffffu, t1, 16);
+                        t2 += __shfl_xor_sync(0xffffffffu, t2, 8);  t2 += __shfl_xor_sync(0xffffffffu, t2, 16);
+                        t3 += __shfl_xor_sync(0xffffffffu, t3, 8);  t3 += __shfl_xor_sync(0xffffffffu, t3, 16);
+                        acc1[0] += t0; acc1[1] += t1; acc1[2] += t2; acc1[3] += t3;
                     }
                 }
             }
@@ -758,7 +805,7 @@ __host__ __device__ constexpr size_t bwd_tc_d_smem(int F) {
 template <int FPK, int FPN>
 __host__ __device__ constexpr size_t bwd_tc_smem(int F) {
     return round_up((int)sizeof(TcBwdESmem<FPK, FPN>), 16) + (size_t)round_up(raw_floats(F), 4) * 4 + 1024 +
-           4 * (size_t)kMnFloats * 4;
+           (size_t)kMnTotal * 4;
 }
 
 template <int FPK, int FPN, int PHASE>

@@ -44,6 +44,7 @@ struct TcPersistSmem {
     uint32_t tmem_base;
     float red[2][2 * FPN + 32];
     double dred[16];
+    alignas(16) float col[kSlots * 4][kColTile];     // statistics pass: per-warp tiles of the column sums (gwtf_tc_fwd.cuh)
 };
 
 // the CTA's contiguous tile range cut into rounds of <= `slots` tiles that never straddle a shape.  Dense mode:
@@ -187,6 +188,9 @@ __global__ void __launch_bounds__(kPersistThreads, 1) k_fwd_layer_tcp(const Laye
         float mv[9];
 #pragma unroll
         for (int i = 0; i < 9; ++i) mv[i] = 0.f;
+        // statistics pass: [net][sum h1, sum h1^2 of channel `lane` | of channel 32 + (lane & 7)], kept across tiles
+        float st_acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+        float* coltile = S.col[warp];
         int cur_b = -1;
         RoundIter it(t_begin, t_end, a.tiles_per_shape, pre, B);
         int base, count, b;
@@ -227,24 +231,41 @@ __global__ void __launch_bounds__(kPersistThreads, 1) k_fwd_layer_tcp(const Laye
 #pragma unroll 1
                 for (int net = 0; net < 2; ++net) {
                     wait_done();                                    // y0
-                    relu_to_operand<FPK, FPN, PASSES>(trow);
+                    relu_to_operand<FPK, FPN>(trow);
                     request();                                      // -> MMA1
                     wait_done();                                    // h1
-                    float h[FPN];
-                    tmem_ld<FPN>(trow + C::D, h);
+                    float h[FPK];                                   // (channels >= F are zero: F < FPK)
+                    tmem_ld<FPK>(trow + C::D, h);
                     tmem_wait_ld();
                     if (net == 0) request();                        // -> MMA0 (net 1): accumulator is in registers now
+                    // per-channel sum h1, sum h1^2 over the warp's 32 points: rows into the warp's tile, lane L sums column L
+                    if (!valid) {
 #pragma unroll
-                    for (int c = 0; c < FPN; c += 16) {
-                        float v[32];
+                        for (int i = 0; i < FPK; ++i) h[i] = 0.f;
+                    }
+                    __syncwarp();
+                    col_write_row<FPK>(coltile, lane, h, 0.f, 0.f);
+                    __syncwarp();
+                    float s1 = 0.f, s2 = 0.f;
+#pragma unroll 8
+                    for (int pp = 0; pp < 32; ++pp) {
+                        const float v = lane < FPK ? coltile[pp * kColPitch + lane] : 0.f;
+                        s1 += v;
+                        s2 = fmaf(v, v, s2);
+                    }
+                    st_acc[net][0] += s1; st_acc[net][1] += s2;
+                    if (FPK > 32) {
+                        float t1 = 0.f, t2 = 0.f;
+                        const int ch = 32 + (lane & 7), p0 = (lane >> 3) * 8;
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) {
-                            const float hv = valid ? h[c + i] : 0.f;
-                            v[2 * i] = hv;
-                            v[2 * i + 1] = hv * hv;
+                        for (int pp = 0; pp < 8; ++pp) {
+                            const float v = ch < FPK ? coltile[(p0 + pp) * kColPitch + ch] : 0.f;
+                            t1 += v;
+                            t2 = fmaf(v, v, t2);
                         }
-                        const float r = warp_reduce_scatter32(v, lane);
-                        atomicAdd(&S.red[net][2 * c + lane], r);
+                        t1 += __shfl_xor_sync(0xffffffffu, t1, 8);  t1 += __shfl_xor_sync(0xffffffffu, t1, 16);
+                        t2 += __shfl_xor_sync(0xffffffffu, t2, 8);  t2 += __shfl_xor_sync(0xffffffffu, t2, 16);
+                        st_acc[net][2] += t1; st_acc[net][3] += t2;
                     }
                 }
             } else {
@@ -288,6 +309,16 @@ __global__ void __launch_bounds__(kPersistThreads, 1) k_fwd_layer_tcp(const Laye
                     mv[0] += x[0]; mv[1] += x[1]; mv[2] += x[2];
                     mv[3] += x[0] * x[0]; mv[4] += x[0] * x[1]; mv[5] += x[0] * x[2];
                     mv[6] += x[1] * x[1]; mv[7] += x[1] * x[2]; mv[8] += x[2] * x[2];
+                }
+            }
+        }
+        if (PHASE == 0) {
+#pragma unroll
+            for (int net = 0; net < 2; ++net) {
+                if (lane < FPK) { atomicAdd(&S.red[net][2 * lane], st_acc[net][0]); atomicAdd(&S.red[net][2 * lane + 1], st_acc[net][1]); }
+                if (lane < 8 && 32 + lane < FPK) {
+                    atomicAdd(&S.red[net][2 * (32 + lane)], st_acc[net][2]);
+                    atomicAdd(&S.red[net][2 * (32 + lane) + 1], st_acc[net][3]);
                 }
             }
         }
