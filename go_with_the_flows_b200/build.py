@@ -26,7 +26,8 @@ def _headers():
 
 
 def _compile(nvcc, src, obj, verbose):
-    cmd = [nvcc] + FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-c', src, '-o', obj]
+    cmd = [nvcc] + FLAGS + os.environ.get('GWTF_NVCC_EXTRA', '').split() + (['-Xptxas', '-v'] if verbose else []) + \
+        ['-c', src, '-o', obj]
     res = subprocess.run(cmd, capture_output=True, text=True)
     return src, res.returncode, res.stdout + res.stderr
 

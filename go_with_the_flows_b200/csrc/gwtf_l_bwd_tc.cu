@@ -32,3 +32,12 @@ int launch_bwd_layer_tc(const BwdArgs& a, int phase, cudaStream_t st) {
 }
 
 }  // namespace gwtf
+
+#ifdef GWTF_STAGE_CLOCKS
+extern "C" int gwtf_debug_stage_clocks(unsigned long long* out, int reset) {
+    cudaDeviceSynchronize();
+    if (out) cudaMemcpyFromSymbol(out, gwtf::g_stage_clk, sizeof(gwtf::g_stage_clk));
+    if (reset) { unsigned long long z[32] = {}; cudaMemcpyToSymbol(gwtf::g_stage_clk, z, sizeof(z)); }
+    return 0;
+}
+#endif

@@ -53,7 +53,6 @@ struct TcBwdESmem {
     TcOperand<FPN, FPK> B1;        // [f][e] folded sd1 | bias column                                       (per shape)
     TcOperand<FPN, FPK> W1T;       // [e][f] = W1[f][e]
     TcOperand<16, FPK> Q0;         // [d][e] = q0[e].d
-    float xd_hi[kBSlots][128 * 8], xd_lo[kBSlots][128 * 8];
     float2 bg[FPN];                // (beta, gamma) of the current shape
     float red[4 * 32];
     alignas(16) float col[kBSlots * 4][kColTile];
@@ -70,8 +69,11 @@ __device__ __forceinline__ uint64_t mn_operand_desc(const float* mn, int arr) {
 template <int N>
 __device__ __forceinline__ void issue_point_contraction(uint32_t d_tmem, const float* mn) {
     const uint32_t idesc = make_idesc_tf32(64, N, 1, 1);
-    const uint64_t ah = mn_operand_desc(mn, 0), al = mn_operand_desc(mn, 1);
-    const uint64_t bh = mn_operand_desc(mn, 2), bl = mn_operand_desc(mn, 3);
+    uint64_t ah = mn_operand_desc(mn, 0), al = mn_operand_desc(mn, 1);
+    uint64_t bh = mn_operand_desc(mn, 2), bl = mn_operand_desc(mn, 3);
+    // opaque to the optimiser: otherwise all 64 per-step descriptors are hoisted out of the tile loop as loop invariants
+    // and spilled (local memory misses the small L1 here), putting a memory round trip in front of every MMA issue
+    asm volatile("" : "+l"(ah), "+l"(al), "+l"(bh), "+l"(bl));
 #pragma unroll
     for (int pass = 0; pass < 3; ++pass) {
         const uint64_t a = pass == 1 ? al : ah;
@@ -89,6 +91,22 @@ __device__ __forceinline__ void store_mn_chunk(float* mn, int arr, int chunk, in
     *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
     *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
 }
+
+// Stage clocks (profiling builds only: GWTF_NVCC_EXTRA=-DGWTF_STAGE_CLOCKS, tools/stage_clocks.py): one compute thread
+// of CTA (0, 0) accumulates the cycles it spends between consecutive marks.
+#ifdef GWTF_STAGE_CLOCKS
+__device__ unsigned long long g_stage_clk[32];
+__shared__ unsigned int s_stage_clk[32];
+#define GWTF_CLK_INIT(cond) const bool clk_on = (cond); unsigned int clk_last = (unsigned int)clock();
+#define GWTF_CLK(i) if (clk_on) { const unsigned int now_ = (unsigned int)clock(); s_stage_clk[i] += now_ - clk_last; clk_last = now_; }
+#define GWTF_CLK_FLUSH() { __syncthreads(); if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < 32) { g_stage_clk[threadIdx.x] += s_stage_clk[threadIdx.x]; } }
+#define GWTF_CLK_ZERO() { if (threadIdx.x < 32) s_stage_clk[threadIdx.x] = 0u; }
+#else
+#define GWTF_CLK_INIT(cond)
+#define GWTF_CLK(i)
+#define GWTF_CLK_FLUSH()
+#define GWTF_CLK_ZERO()
+#endif
 
 template <int FPK, int FPN>
 __device__ __forceinline__ void bwd_tc_phase1(const BwdArgs& a, unsigned char* smem_raw) {
@@ -125,7 +143,6 @@ __device__ __forceinline__ void bwd_tc_phase1(const BwdArgs& a, unsigned char* s
         mbar_init(&S.buf_free, 1);
         mbar_fence_init();
     }
-    for (int i = tid; i < kBSlots * 128 * 8; i += kBwdThreads) { (&S.xd_hi[0][0])[i] = 0.f; (&S.xd_lo[0][0])[i] = 0.f; }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -203,8 +220,8 @@ __device__ __forceinline__ void bwd_tc_phase1(const BwdArgs& a, unsigned char* s
 #pragma unroll 1
                 for (int t = 0; t < tiles_s; ++t) {
                     mbar_wait(&S.req[s], req_phase); req_phase ^= 1u; tc_fence_after();
-                    issue_ss_k8<FPN>(ts + C::D, S.xd_hi[s], S.xd_lo[s], S.B0.hi, S.B0.lo);
-                    issue_ss_k8<FPN>(ts + C::P, S.xd_hi[s], S.xd_lo[s], S.PW.hi, S.PW.lo);
+                    issue_ts<8, FPN>(ts + C::D, ts + C::Ahi, ts + C::Alo, S.B0.hi, S.B0.lo);
+                    issue_ts<8, FPN>(ts + C::P, ts + C::Ahi, ts + C::Alo, S.PW.hi, S.PW.lo);
                     tc_commit(&S.done[s]);
                     mbar_wait(&S.req[s], req_phase); req_phase ^= 1u; tc_fence_after();
                     issue_ts<FPK, FPN>(ts + C::D, ts + C::Ahi, ts + C::Alo, S.B1.hi, S.B1.lo);
@@ -244,7 +261,30 @@ __device__ __forceinline__ void bwd_tc_phase1(const BwdArgs& a, unsigned char* s
             float* coltile = S.col[warp];
             int cur_b = -1;
             int seq = net * my_tiles;              // sequence number of this CTA's point contractions (buffer turns)
+            GWTF_CLK_INIT(blockIdx.x == 0 && blockIdx.y == 0 && tid == 0)
             RoundIter it(t_begin, t_end, tps, nullptr, B, kBSlots);
+            // a second iterator runs one round ahead: the global loads of the next tile (x, dO, incoming gradient) are in
+            // flight while this tile is processed
+            RoundIter ahead(t_begin, t_end, tps, nullptr, B, kBSlots);
+            float pf[9];
+            auto prefetch = [&]() {
+                int pbase, pcount, pb;
+#pragma unroll
+                for (int i = 0; i < 9; ++i) pf[i] = 0.f;
+                if (!ahead.next(pbase, pcount, pb) || slot >= pcount) return;
+                const int pn = (pbase + slot - ahead.shape_begin()) * 128 + wtid;
+                if (pn >= N) return;
+                const float* pxin = a.xin_shared ? a.xin + (size_t)pb * 3 * N : a.xin + ((size_t)j * B + pb) * 3 * N;
+                const float* pdob = a.dobuf + ((size_t)j * B + pb) * 6 * N + (size_t)net * 3 * N;
+                const float* pg = a.gbuf + ((size_t)j * B + pb) * 3 * N;
+#pragma unroll
+                for (int d = 0; d < 3; ++d) {
+                    pf[d] = pxin[(size_t)d * N + pn];
+                    pf[3 + d] = pdob[(size_t)d * N + pn];
+                    pf[6 + d] = pg[(size_t)d * N + pn];
+                }
+            };
+            prefetch();
             int base, count, b;
             while (it.next(base, count, b)) {
                 if (b != cur_b) {
@@ -283,119 +323,158 @@ __device__ __forceinline__ void bwd_tc_phase1(const BwdArgs& a, unsigned char* s
                     fence_proxy_async();
                     bwd_compute_barrier();
                     cur_b = b;
+                    GWTF_CLK(12)
                 }
                 const int my_seq = seq + slot;
                 seq += count;
-                if (slot >= count) continue;
+                if (slot >= count) { prefetch(); continue; }
                 const int t = base + slot;
                 const int n = (t - it.shape_begin()) * 128 + wtid;
                 const bool valid = n < N;
-                const float* xin = a.xin_shared ? a.xin + (size_t)b * 3 * N : a.xin + ((size_t)j * B + b) * 3 * N;
                 const size_t sb = ((size_t)j * B + b) * 3 * N;
-                const float* dob = a.dobuf + ((size_t)j * B + b) * 6 * N + (size_t)net * 3 * N;
                 float x[3], dO[3], gold[3];
 #pragma unroll
-                for (int d = 0; d < 3; ++d) {
-                    x[d] = valid ? xin[(size_t)d * N + n] : 0.f;
-                    dO[d] = valid ? dob[(size_t)d * N + n] : 0.f;
-                    gold[d] = valid ? a.gbuf[sb + (size_t)d * N + n] : 0.f;
-                }
-                {   // the (x, 1 | dO) operand row of this point
-                    float h[6], lo[6];
+                for (int d = 0; d < 3; ++d) { x[d] = pf[d]; dO[d] = pf[3 + d]; gold[d] = pf[6 + d]; }
+                {   // the (x, 1 | dO) operand row of this point, in tensor memory where a0 will go once y0 has been read:
+                    // no shared-memory write, hence no proxy fence (MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC, ~1000 cycles here)
+                    float h[8], lo[8];
 #pragma unroll
-                    for (int d = 0; d < 3; ++d) { split_tf32(x[d], h[d], lo[d]); split_tf32(dO[d], h[3 + d], lo[3 + d]); }
-                    const int off = kmajor_offset(wtid, 0, 8);
-                    *reinterpret_cast<float4*>(S.xd_hi[slot] + off) = make_float4(h[0], h[1], h[2], 1.0f);
-                    *reinterpret_cast<float4*>(S.xd_hi[slot] + off + 32) = make_float4(h[3], h[4], h[5], 0.0f);
-                    *reinterpret_cast<float4*>(S.xd_lo[slot] + off) = make_float4(lo[0], lo[1], lo[2], 0.0f);
-                    *reinterpret_cast<float4*>(S.xd_lo[slot] + off + 32) = make_float4(lo[3], lo[4], lo[5], 0.0f);
+                    for (int d = 0; d < 3; ++d) { split_tf32(x[d], h[d], lo[d]); split_tf32(dO[d], h[4 + d], lo[4 + d]); }
+                    h[3] = 1.0f; lo[3] = 0.f; h[7] = 0.f; lo[7] = 0.f;
+                    tmem_st8(trow + C::Ahi, h);
+                    tmem_st8(trow + C::Alo, lo);
+                    tmem_wait_st();
                 }
-                fence_proxy_async();
+                GWTF_CLK(0)
                 request();                                              // -> batch A: y0, P
                 wait_done();
+                GWTF_CLK(1)
                 uint32_t m0lo = 0u, m0hi = 0u;                          // [y0 > 0], channel c -> bit c
-#pragma unroll
-                for (int c = 0; c < FPK; c += 8) {
-                    float y[8], hi[8], lo[8];
-                    tmem_ld8(trow + C::D + c, y);
+                {
+                    float y[FPK];
+                    tmem_ld<FPK>(trow + C::D, y);                       // one round trip for the whole row
                     tmem_wait_ld();
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const bool pos = y[i] > 0.f;
-                        if (c + i < 32) m0lo |= pos ? (1u << (c + i)) : 0u; else m0hi |= pos ? (1u << (c + i - 32)) : 0u;
-                        split_tf32(fmaxf(y[i], 0.f), hi[i], lo[i]);
+                    for (int c = 0; c < FPK; c += 8) {
+                        float hi[8], lo[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const bool pos = y[c + i] > 0.f;
+                            if (c + i < 32) m0lo |= pos ? (1u << (c + i)) : 0u; else m0hi |= pos ? (1u << (c + i - 32)) : 0u;
+                            split_tf32(fmaxf(y[c + i], 0.f), hi[i], lo[i]);
+                        }
+                        tmem_st8(trow + C::Ahi + c, hi);
+                        tmem_st8(trow + C::Alo + c, lo);
                     }
-                    tmem_st8(trow + C::Ahi + c, hi);
-                    tmem_st8(trow + C::Alo + c, lo);
                 }
                 tmem_wait_st();
+                GWTF_CLK(2)
                 request();                                              // -> batch B: y1
                 wait_done();
-                // r = dh1, written over the y1 / P columns it was computed from (hi -> D, lo -> P): the a0 operand stays
-                // intact for the point contraction, and nothing here needs the shared operand buffer yet
+                GWTF_CLK(3)
+                // r = dh1 = [y1 > 0] P + beta y1 + gamma, written over the y1 / P columns it was computed from (hi -> D,
+                // lo -> P) for the da0 MMA, and together with a0 into the shared point-contraction operands.  Sixteen
+                // channels per tensor-memory round trip; the operand-buffer turn (contraction my_seq - 1 consumed) is
+                // only needed from the first shared-memory store on.
+                bool have_turn = false;
 #pragma unroll
-                for (int c = 0; c < FPK; c += 8) {
-                    float y1[8], p8[8], rh[8], rl[8];
-                    tmem_ld8(trow + C::D + c, y1);
-                    tmem_ld8(trow + C::P + c, p8);
+                for (int c0 = 0; c0 < FPK; c0 += 16) {
+                    constexpr int kMax = 16;
+                    const int nch = FPK - c0 < kMax ? FPK - c0 : kMax;                  // 16, 16, 8 (compile time after unrolling)
+                    float y1[kMax], p8[kMax];
+                    if (nch == 16) { tmem_ld16(trow + C::D + c0, y1); tmem_ld16(trow + C::P + c0, p8); }
+                    else { tmem_ld8(trow + C::D + c0, y1); tmem_ld8(trow + C::P + c0, p8); }
+                    tmem_wait_ld();
+                    float rh[kMax], rl[kMax];
+#pragma unroll
+                    for (int i = 0; i < kMax; i += 2) {
+                        if (i < nch) {
+                            const float4 g2 = *reinterpret_cast<const float4*>(&S.bg[c0 + i]);  // (beta, gamma) x 2
+                            float r0 = fmaf(g2.x, y1[i], g2.y) + (y1[i] > 0.f ? p8[i] : 0.f);
+                            float r1 = fmaf(g2.z, y1[i + 1], g2.w) + (y1[i + 1] > 0.f ? p8[i + 1] : 0.f);
+                            if (!valid) { r0 = 0.f; r1 = 0.f; }
+                            split_tf32(r0, rh[i], rl[i]);
+                            split_tf32(r1, rh[i + 1], rl[i + 1]);
+                        }
+                    }
+                    float ah[kMax], al[kMax];                           // a0 of these channels: in flight during the r stores
+                    if (nch == 16) { tmem_ld16(trow + C::Ahi + c0, ah); tmem_ld16(trow + C::Alo + c0, al); }
+                    else { tmem_ld8(trow + C::Ahi + c0, ah); tmem_ld8(trow + C::Alo + c0, al); }
+#pragma unroll
+                    for (int c = 0; c < kMax; c += 8) {
+                        if (c < nch) {
+                            tmem_st8(trow + C::D + c0 + c, rh + c);
+                            tmem_st8(trow + C::P + c0 + c, rl + c);
+                        }
+                    }
+                    if (!have_turn) {
+                        GWTF_CLK(4)
+                        if (my_seq > 0) mbar_wait(&S.buf_free, (uint32_t)((my_seq - 1) & 1));
+                        have_turn = true;
+                        GWTF_CLK(5)
+                    }
+#pragma unroll
+                    for (int c = 0; c < kMax; c += 8) {
+                        if (c < nch) {
+                            float t8[8];
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) t8[i] = rh[c + i];
+                            store_mn_chunk(mn, 0, (c0 + c) >> 3, wtid, t8);
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) t8[i] = rl[c + i];
+                            store_mn_chunk(mn, 1, (c0 + c) >> 3, wtid, t8);
+                        }
+                    }
                     tmem_wait_ld();
 #pragma unroll
-                    for (int i = 0; i < 8; i += 2) {
-                        const float4 g2 = *reinterpret_cast<const float4*>(&S.bg[c + i]);      // (beta, gamma) x 2
-                        float r0 = fmaf(g2.x, y1[i], g2.y) + (y1[i] > 0.f ? p8[i] : 0.f);
-                        float r1 = fmaf(g2.z, y1[i + 1], g2.w) + (y1[i + 1] > 0.f ? p8[i + 1] : 0.f);
-                        if (!valid) { r0 = 0.f; r1 = 0.f; }
-                        split_tf32(r0, rh[i], rl[i]);
-                        split_tf32(r1, rh[i + 1], rl[i + 1]);
+                    for (int c = 0; c < kMax; c += 8) {
+                        if (c < nch) {
+                            float t8[8];
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) t8[i] = ah[c + i];
+                            store_mn_chunk(mn, 2, (c0 + c) >> 3, wtid, t8);
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) t8[i] = al[c + i];
+                            store_mn_chunk(mn, 3, (c0 + c) >> 3, wtid, t8);
+                        }
                     }
-                    tmem_st8(trow + C::D + c, rh);
-                    tmem_st8(trow + C::P + c, rl);
                 }
                 tmem_wait_st();
-                // our turn on the point-contraction operands (contraction number my_seq - 1 has been consumed); the turn
-                // only covers the copy TMEM -> shared memory and the MMA chain that reads it
-                if (my_seq > 0) mbar_wait(&S.buf_free, (uint32_t)((my_seq - 1) & 1));
-#pragma unroll
-                for (int c = 0; c < FPK; c += 8) {
-                    float rh[8], rl[8], ah[8], al[8];
-                    tmem_ld8(trow + C::D + c, rh);
-                    tmem_ld8(trow + C::P + c, rl);
-                    tmem_ld8(trow + C::Ahi + c, ah);
-                    tmem_ld8(trow + C::Alo + c, al);
-                    tmem_wait_ld();
-                    store_mn_chunk(mn, 0, c >> 3, wtid, rh);
-                    store_mn_chunk(mn, 1, c >> 3, wtid, rl);
-                    store_mn_chunk(mn, 2, c >> 3, wtid, ah);
-                    store_mn_chunk(mn, 3, c >> 3, wtid, al);
-                }
                 tc_fence_before();
                 fence_proxy_async();
+                GWTF_CLK(6)
                 request();                                              // -> batch C: da0, then dW1 += r^T a0
+                // (the proxy fence above is a MEMBAR.ALL.CTA in SASS and would wait for these loads: issue them after it,
+                // with the rest of the tile to land in)
+                prefetch();
                 wait_done();                                            // (da0 only: dW1 keeps running)
+                GWTF_CLK(7)
                 {
                     const float xa = keepd[0] == 0 ? x[0] : (keepd[0] == 1 ? x[1] : x[2]);
                     const float xb = k == 2 ? (keepd[1] == 0 ? x[0] : (keepd[1] == 1 ? x[1] : x[2])) : 0.f;
                     // dy0 = [y0 > 0] da0 -> operand (hi -> D, lo -> P) and, raw, into row `lane` of the warp's column tile
-                    __syncwarp();
+                    float dy[FPK];
+                    tmem_ld<FPK>(trow + C::Ahi, dy);
+                    tmem_wait_ld();
+                    __syncwarp();                                       // the previous tile's column readers are done
                     float4* crow = reinterpret_cast<float4*>(coltile + lane * kColPitch);
 #pragma unroll
                     for (int c = 0; c < FPK; c += 8) {
-                        float d8[8], hi[8], lo[8];
-                        tmem_ld8(trow + C::Ahi + c, d8);
-                        tmem_wait_ld();
+                        float hi[8], lo[8];
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
                             const bool pos = (c + i < 32) ? ((m0lo >> (c + i)) & 1u) : ((m0hi >> (c + i - 32)) & 1u);
-                            d8[i] = pos ? d8[i] : 0.f;
-                            split_tf32(d8[i], hi[i], lo[i]);
+                            dy[c + i] = pos ? dy[c + i] : 0.f;
+                            split_tf32(dy[c + i], hi[i], lo[i]);
                         }
                         tmem_st8(trow + C::D + c, hi);
                         tmem_st8(trow + C::P + c, lo);
-                        crow[c / 4] = make_float4(d8[0], d8[1], d8[2], d8[3]);
-                        crow[c / 4 + 1] = make_float4(d8[4], d8[5], d8[6], d8[7]);
+                        crow[c / 4] = make_float4(dy[c], dy[c + 1], dy[c + 2], dy[c + 3]);
+                        crow[c / 4 + 1] = make_float4(dy[c + 4], dy[c + 5], dy[c + 6], dy[c + 7]);
                     }
                     *reinterpret_cast<float2*>(coltile + 32 * kColPitch + 2 * lane) = make_float2(xa, xb);
                     tmem_wait_st();
+                    GWTF_CLK(8)
                     request();                                          // -> batch D: du
                     // sums of dy0 (1 | xa | xb) over the warp's 32 points: lane L sums column L
                     __syncwarp();
@@ -425,7 +504,9 @@ __device__ __forceinline__ void bwd_tc_phase1(const BwdArgs& a, unsigned char* s
                         acc1[0] += t0; acc1[1] += t1; acc1[2] += t2;
                     }
                 }
+                GWTF_CLK(9)
                 wait_done();
+                GWTF_CLK(10)
                 {
                     float du[8];
                     tmem_ld8(trow + C::Ahi, du);
@@ -435,10 +516,12 @@ __device__ __forceinline__ void bwd_tc_phase1(const BwdArgs& a, unsigned char* s
                         for (int d = 0; d < 3; ++d) a.gbuf[sb + (size_t)d * N + n] = gold[d] + du[d];
                     }
                 }
+                GWTF_CLK(11)
             }
             // ---- drain this slot's MMAs (the dW1 chain of the last tile included)
             request();
             wait_done();
+            GWTF_CLK(13)
 #pragma unroll
             for (int q = 0; q < 3; ++q) {
                 if (lane < FPK) atomicAdd(&S.red[q * FPK + lane], acc0[q]);
@@ -663,6 +746,7 @@ __device__ __forceinline__ void bwd_tc_phase0(const BwdArgs& a, unsigned char* s
             };
 
             int cur_b = -1;
+            GWTF_CLK_INIT(blockIdx.x == 0 && blockIdx.y == 0 && tid == 0)
             RoundIter it(t_begin, t_end, tps, nullptr, B, kDSlots);
             int base, count, b;
             while (it.next(base, count, b)) {
@@ -675,6 +759,7 @@ __device__ __forceinline__ void bwd_tc_phase0(const BwdArgs& a, unsigned char* s
                     fence_proxy_async();
                     bwd_d_barrier();
                     cur_b = b;
+                    GWTF_CLK(24)
                 }
                 if (slot >= count) continue;
                 const int t = base + slot;
@@ -706,11 +791,15 @@ __device__ __forceinline__ void bwd_tc_phase0(const BwdArgs& a, unsigned char* s
                 }
                 write_x_operand(S.x_hi[slot], S.x_lo[slot], x, wtid);
                 fence_proxy_async();
+                GWTF_CLK(16)
                 request();                                              // -> y0
                 wait_done();
+                GWTF_CLK(17)
                 relu_to_operand<FPK, FPN>(trow);
+                GWTF_CLK(18)
                 request();                                              // -> y1
                 wait_done();
+                GWTF_CLK(19)
                 float y1[FPK];
                 tmem_ld<FPK>(trow + C::D, y1);
                 tmem_wait_ld();
@@ -725,8 +814,10 @@ __device__ __forceinline__ void bwd_tc_phase0(const BwdArgs& a, unsigned char* s
                         tmem_st8(trow + C::Alo + c, lo);
                     }
                     tmem_wait_st();
+                    GWTF_CLK(20)
                     request();                                          // -> o
                     wait_done();
+                    GWTF_CLK(21)
                     float ov[8];
                     tmem_ld8(trow + C::D, ov);
                     tmem_wait_ld();
@@ -749,6 +840,7 @@ __device__ __forceinline__ void bwd_tc_phase0(const BwdArgs& a, unsigned char* s
                         dO[d] = dov;
                     }
                 }
+                GWTF_CLK(22)
                 // ---- sums over the warp's 32 points: rows of a1 into the warp's tile, columns summed by the reader lanes.
                 // The constant-one channel F has a1 = 1, so its a1 dA / a1 dB sums ARE the sd2 bias gradients.
                 const float dA = wd[0] == 0 ? dO[0] : (wd[0] == 1 ? dO[1] : dO[2]);
@@ -786,10 +878,13 @@ __device__ __forceinline__ void bwd_tc_phase0(const BwdArgs& a, unsigned char* s
                         acc1[0] += t0; acc1[1] += t1; acc1[2] += t2; acc1[3] += t3;
                     }
                 }
+                GWTF_CLK(23)
             }
             if (cur_b >= 0) flush_shape(cur_b);
+            GWTF_CLK(24)
             request();                                                  // drain
             wait_done();
+            GWTF_CLK(25)
         }
     }
     tc_fence_before();
@@ -811,8 +906,10 @@ __host__ __device__ constexpr size_t bwd_tc_smem(int F) {
 template <int FPK, int FPN, int PHASE>
 __global__ void __launch_bounds__(PHASE == 0 ? kBwdDThreads : kBwdThreads, 1) k_bwd_layer_tc(const BwdArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
+    GWTF_CLK_ZERO()
     if constexpr (PHASE == 0) bwd_tc_phase0<FPK, FPN>(a, smem_raw);
     else bwd_tc_phase1<FPK, FPN>(a, smem_raw);
+    GWTF_CLK_FLUSH()
 }
 
 }  // namespace gwtf
