@@ -270,7 +270,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) k_fwd_layer_tcp(const Laye
                 }
             } else {
                 float o3[2][3];
-#pragma unroll 1
+#pragma unroll                                                      // (unrolled: o3[net] stays in registers)
                 for (int net = 0; net < 2; ++net) {
                     wait_done();                                    // y0
                     relu_to_operand<FPK, FPN, PASSES>(trow);
