@@ -88,8 +88,12 @@ __device__ __forceinline__ void issue_point_contraction(uint32_t d_tmem, const f
 __device__ __forceinline__ void store_mn_chunk(float* mn, int arr, int chunk, int p, const float (&v)[8]) {
     float* dst = chunk < 4 ? mn + arr * kMnFloats + mnmajor_sw32_offset(8 * chunk, p, 128)
                            : mn + 4 * kMnFloats + (p >> 2) * 128 + (p & 3) * 32 + ((arr ^ (p & 3)) << 3);
-    *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
-    *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    // The 8 lanes that share p & 3 land in the same 32-byte bank window (rows 512 B apart): half of them store the upper
+    // 16 bytes first, so each instruction covers all 32 banks (4 wavefronts instead of 8).
+    const bool odd = (p >> 2) & 1;
+    const float4 a = make_float4(v[0], v[1], v[2], v[3]), b = make_float4(v[4], v[5], v[6], v[7]);
+    *reinterpret_cast<float4*>(dst + (odd ? 4 : 0)) = odd ? b : a;
+    *reinterpret_cast<float4*>(dst + (odd ? 0 : 4)) = odd ? a : b;
 }
 
 // Stage clocks (profiling builds only: GWTF_NVCC_EXTRA=-DGWTF_STAGE_CLOCKS, tools/stage_clocks.py): one compute thread
