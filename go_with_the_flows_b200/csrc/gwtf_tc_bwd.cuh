@@ -179,18 +179,21 @@ __device__ __forceinline__ void bwd_tc_phase1(const BwdArgs& a, unsigned char* s
         // ---- operands of this net that do not depend on the shape
         __syncthreads();              // everybody is done with the previous net's operands
         for (int i = tid; i < FPN * 8; i += kBwdThreads) {                     // B0 (as stage_b0)
-            const int e = i >> 3, kk = i & 7;
+            int e, kk;
+            TcOperand<FPN, 8>::coords(i, e, kk);
             float v = 0.f;
             if (e < F) { const float4 q = S.W.q0[net][e]; v = kk == 0 ? q.x : (kk == 1 ? q.y : (kk == 2 ? q.z : (kk == 3 ? q.w : 0.f))); }
             else if (e == F && kk == 3) v = 1.f;
             S.B0.set(e, kk, v);
         }
         for (int i = tid; i < FPN * FPK; i += kBwdThreads) {                   // W1T[e][f] = W1[f][e]
-            const int e = i / FPK, f = i - e * FPK;
+            int e, f;
+            TcOperand<FPN, FPK>::coords(i, e, f);
             S.W1T.set(e, f, (e < F && f < F) ? raw[net * o.stride + o.W1 + f * F + e] : 0.f);
         }
         for (int i = tid; i < 16 * FPK; i += kBwdThreads) {                    // Q0[d][e] = q0[e].d
-            const int d = i / FPK, e = i - d * FPK;
+            int d, e;
+            TcOperand<16, FPK>::coords(i, d, e);
             float v = 0.f;
             if (d < 3 && e < F) { const float4 q = S.W.q0[net][e]; v = d == 0 ? q.x : (d == 1 ? q.y : q.z); }
             S.Q0.set(d, e, v);
@@ -297,7 +300,8 @@ __device__ __forceinline__ void bwd_tc_phase1(const BwdArgs& a, unsigned char* s
                     stage_film<FPN, true>(S.W, &S.WB, a.film + ((size_t)(b * K + j) * L + l) * 4 * F, F, tid, CT);
                     bwd_compute_barrier();
                     for (int i = tid; i < FPN * FPK; i += CT) {                // B1 (as stage_b1 with the FiLM fold)
-                        const int f = i / FPK, e = i - f * FPK;
+                        int f, e;
+                        TcOperand<FPN, FPK>::coords(i, f, e);
                         float v = 0.f;
                         if (f < F) {
                             if (e < F) v = S.W.st[net][f].x * raw[net * o.stride + o.W1 + f * F + e];
@@ -306,7 +310,8 @@ __device__ __forceinline__ void bwd_tc_phase1(const BwdArgs& a, unsigned char* s
                         S.B1.set(f, e, v);
                     }
                     for (int i = tid; i < FPN * 8; i += CT) {                  // PW[f][4+d] = (s/sigma1) w2[f].d
-                        const int f = i >> 3, kk = i & 7;
+                        int f, kk;
+                        TcOperand<FPN, 8>::coords(i, f, kk);
                         float v = 0.f;
                         if (f < F && kk >= 4 && kk < 7) {
                             const float4 w2 = S.W.w2[net][f];
@@ -493,11 +498,11 @@ __device__ __forceinline__ void bwd_tc_phase1(const BwdArgs& a, unsigned char* s
                     }
                     if (FPK > 32) {
                         float t0 = 0.f, t1 = 0.f, t2 = 0.f;
-                        const int ch = 32 + (lane & 7), p0 = (lane >> 3) * 8;
+                        const int ch = 32 + (lane & 7), grp = lane >> 3;
 #pragma unroll
                         for (int pp = 0; pp < 8; ++pp) {
-                            const float v = ch < FPK ? coltile[(p0 + pp) * kColPitch + ch] : 0.f;
-                            const float2 x2 = *reinterpret_cast<const float2*>(wts + 2 * (p0 + pp));
+                            const float v = ch < FPK ? coltile[col_tail_point(grp, pp) * kColPitch + ch] : 0.f;
+                            const float2 x2 = *reinterpret_cast<const float2*>(wts + 2 * col_tail_point(grp, pp));
                             t0 += v;
                             t1 = fmaf(v, x2.x, t1);
                             t2 = fmaf(v, x2.y, t2);
@@ -866,11 +871,11 @@ __device__ __forceinline__ void bwd_tc_phase0(const BwdArgs& a, unsigned char* s
                     }
                     if (FPK > 32) {
                         float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
-                        const int ch = 32 + (lane & 7), p0 = (lane >> 3) * 8;
+                        const int ch = 32 + (lane & 7), grp = lane >> 3;
 #pragma unroll
                         for (int pp = 0; pp < 8; ++pp) {
-                            const float v = ch < FPK ? coltile[(p0 + pp) * kColPitch + ch] : 0.f;
-                            const float2 d2 = *reinterpret_cast<const float2*>(wts + 2 * (p0 + pp));
+                            const float v = ch < FPK ? coltile[col_tail_point(grp, pp) * kColPitch + ch] : 0.f;
+                            const float2 d2 = *reinterpret_cast<const float2*>(wts + 2 * col_tail_point(grp, pp));
                             t0 = fmaf(v, d2.x, t0);
                             t1 = fmaf(v, d2.y, t1);
                             if (v > 0.f) { t2 += d2.x; t3 += d2.y; }

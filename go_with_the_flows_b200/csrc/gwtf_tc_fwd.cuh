@@ -54,6 +54,14 @@ struct TcOperand {          // UMMA smem operand, K-major, 3xTF32 split
         hi[off] = h;
         lo[off] = l;
     }
+    // element (row, k) stored at float offset i: a staging loop that walks i has its 32 lanes on 32 distinct banks (walking
+    // rows x k instead puts 8 lanes on one bank: consecutive k-quads are 32 floats apart)
+    static __device__ __forceinline__ void coords(int i, int& row, int& k) {
+        const int blk = i >> 5, lane = i & 31;
+        const int rg = blk / (KT / 4), kg = blk - rg * (KT / 4);
+        row = rg * 8 + (lane >> 2);
+        k = kg * 4 + (lane & 3);
+    }
 };
 
 template <int FPK, int FPN>
@@ -67,7 +75,8 @@ struct TcLayerOps {         // operands of one net
 template <int FPK, int FPN>
 __device__ __forceinline__ void stage_b0(TcLayerOps<FPK, FPN>& O, const float4* q0, int F, int tid, int nthreads) {
     for (int i = tid; i < FPN * 8; i += nthreads) {
-        const int e = i >> 3, k = i & 7;
+        int e, k;
+        TcOperand<FPN, 8>::coords(i, e, k);
         float v = 0.f;
         if (e < F) {
             const float4 q = q0[e];
@@ -81,7 +90,8 @@ template <int FPK, int FPN>
 __device__ __forceinline__ void stage_b1(TcLayerOps<FPK, FPN>& O, const float* w1, const float2* st, int F, int tid,
                                          int nthreads) {
     for (int i = tid; i < FPN * FPK; i += nthreads) {
-        const int f = i / FPK, e = i - f * FPK;
+        int f, e;
+        TcOperand<FPN, FPK>::coords(i, f, e);
         float v = 0.f;
         if (f < F) {
             if (e < F) v = st ? st[f].x * w1[f * F + e] : w1[f * F + e];
@@ -95,7 +105,8 @@ template <int FPK, int FPN>
 __device__ __forceinline__ void stage_b2(TcLayerOps<FPK, FPN>& O, const float4* w2, float4 b2, int F, int tid,
                                          int nthreads) {
     for (int i = tid; i < 16 * FPK; i += nthreads) {
-        const int d = i / FPK, f = i - d * FPK;
+        int d, f;
+        TcOperand<16, FPK>::coords(i, d, f);
         float v = 0.f;
         if (d < 3) {
             if (f < F) { const float4 w = w2[f]; v = d == 0 ? w.x : (d == 1 ? w.y : w.z); }
@@ -224,7 +235,9 @@ __device__ __forceinline__ void col_write_row(float* tile, int lane, const float
     *reinterpret_cast<float2*>(tile + 32 * kColPitch + 2 * lane) = make_float2(wA, wB);
 }
 // channel this lane accumulates in the two reader passes: pass 0 -> lane, pass 1 -> 32 + (lane & 7) (complete in
-// every lane after the shuffles; lanes >= 8 hold copies)
+// every lane after the shuffles; lanes >= 8 hold copies).  In pass 1 lane group g = lane >> 3 reads the points below:
+// at every step the four groups are 6 (or 2) rows apart, i.e. 8 / 24 banks, so the 32 lanes hit 32 distinct banks.
+__device__ __forceinline__ int col_tail_point(int g, int pp) { return pp < 6 ? 6 * g + pp : 24 + 2 * g + (pp - 6); }
 
 // CTA-wide hand-off: everything written (TMEM / smem) by all threads is visible to the MMA issuer
 __device__ __forceinline__ void tc_handoff() {

@@ -256,10 +256,10 @@ __global__ void __launch_bounds__(kPersistThreads, 1) k_fwd_layer_tcp(const Laye
                     st_acc[net][0] += s1; st_acc[net][1] += s2;
                     if (FPK > 32) {
                         float t1 = 0.f, t2 = 0.f;
-                        const int ch = 32 + (lane & 7), p0 = (lane >> 3) * 8;
+                        const int ch = 32 + (lane & 7), grp = lane >> 3;
 #pragma unroll
                         for (int pp = 0; pp < 8; ++pp) {
-                            const float v = ch < FPK ? coltile[(p0 + pp) * kColPitch + ch] : 0.f;
+                            const float v = ch < FPK ? coltile[col_tail_point(grp, pp) * kColPitch + ch] : 0.f;
                             t1 += v;
                             t2 = fmaf(v, v, t2);
                         }
