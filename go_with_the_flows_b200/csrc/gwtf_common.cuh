@@ -248,6 +248,39 @@ __device__ __forceinline__ void stage_film(WT& W, WBT* WB, const float* film, in
     }
 }
 
+// The same fold with the 4F FiLM values of the NEXT shape already in registers (one (s, t) pair in each of the first 2 FP
+// threads): a persistent kernel restages per shape behind a barrier of all its compute warps, and the global-load latency
+// of these few values would otherwise be paid there, by everybody, at every shape boundary.
+template <int FP>
+struct FilmAhead {
+    float s, t;
+    int b;                  // shape the pair belongs to
+    __device__ __forceinline__ void fetch(const float* film_all, int bb, int B, int K, int j, int L, int l, int F, int tid) {
+        b = bb; s = 0.f; t = 0.f;
+        if (tid < 2 * FP && bb < B) {
+            const int net = tid / FP, c = tid - net * FP;
+            if (c < F) {
+                const float* f = film_all + ((size_t)(bb * K + j) * L + l) * 4 * F + net * 2 * F + c;
+                s = f[0];
+                t = f[F];
+            }
+        }
+    }
+    template <bool BWD, class WT, class WBT>
+    __device__ __forceinline__ void stage(WT& W, WBT* WB, int F, int tid) const {
+        if (tid < 2 * FP) {
+            const int net = tid / FP, c = tid - net * FP;
+            float2 st = make_float2(0.f, 0.f);
+            if (c < F) {
+                const float2 mi = W.mi1[net][c];
+                st = make_float2(s * mi.y, t - s * mi.x);
+            }
+            W.st[net][c] = st;
+            if (BWD) WB->sg[net][c].x = s;
+        }
+    }
+};
+
 // ---------------------------------------------------------------------------------------------
 // per-point microkernel
 // ---------------------------------------------------------------------------------------------

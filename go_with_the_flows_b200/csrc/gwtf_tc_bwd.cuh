@@ -270,6 +270,9 @@ __device__ __forceinline__ void bwd_tc_phase1(const BwdArgs& a, unsigned char* s
             int seq = net * my_tiles;              // sequence number of this CTA's point contractions (buffer turns)
             GWTF_CLK_INIT(blockIdx.x == 0 && blockIdx.y == 0 && tid == 0)
             RoundIter it(t_begin, t_end, tps, nullptr, B, kBSlots);
+            FilmAhead<FPN> film;
+            film.b = -1; film.s = 0.f; film.t = 0.f;
+            if (t_begin < t_end) film.fetch(a.film, it.b, B, K, j, L, l, F, tid);
             // a second iterator runs one round ahead: the global loads of the next tile (x, dO, incoming gradient) are in
             // flight while this tile is processed
             RoundIter ahead(t_begin, t_end, tps, nullptr, B, kBSlots);
@@ -297,7 +300,9 @@ __device__ __forceinline__ void bwd_tc_phase1(const BwdArgs& a, unsigned char* s
                 if (b != cur_b) {
                     // new shape: every warpgroup has drained the MMAs that read the per-shape operands
                     bwd_compute_barrier();
-                    stage_film<FPN, true>(S.W, &S.WB, a.film + ((size_t)(b * K + j) * L + l) * 4 * F, F, tid, CT);
+                    if (film.b != b) film.fetch(a.film, b, B, K, j, L, l, F, tid);
+                    film.template stage<true>(S.W, &S.WB, F, tid);
+                    film.fetch(a.film, b + 1, B, K, j, L, l, F, tid);  // in flight until the next shape boundary
                     bwd_compute_barrier();
                     for (int i = tid; i < FPN * FPK; i += CT) {                // B1 (as stage_b1 with the FiLM fold)
                         int f, e;

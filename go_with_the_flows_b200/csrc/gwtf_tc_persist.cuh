@@ -193,12 +193,17 @@ __global__ void __launch_bounds__(kPersistThreads, 1) k_fwd_layer_tcp(const Laye
         float* coltile = S.col[warp];
         int cur_b = -1;
         RoundIter it(t_begin, t_end, a.tiles_per_shape, pre, B);
+        FilmAhead<FPN> film;
+        film.b = -1; film.s = 0.f; film.t = 0.f;
+        if (PHASE == 1 && t_begin < t_end) film.fetch(a.film, it.b, B, K, j, L, l, F, tid);
         int base, count, b;
         while (it.next(base, count, b)) {
             if (PHASE == 1 && b != cur_b) {
                 // new shape: every warpgroup has drained its MMAs (it waited on `done` for each request)
                 compute_barrier();
-                stage_film<FPN, false>(S.W, (LayerWB<FPN>*)nullptr, a.film + ((size_t)(b * K + j) * L + l) * 4 * F, F, tid, CT);
+                if (film.b != b) film.fetch(a.film, b, B, K, j, L, l, F, tid);
+                film.template stage<false>(S.W, (LayerWB<FPN>*)nullptr, F, tid);
+                film.fetch(a.film, b + 1, B, K, j, L, l, F, tid);      // in flight until the next shape boundary
                 compute_barrier();
 #pragma unroll
                 for (int net = 0; net < 2; ++net)
