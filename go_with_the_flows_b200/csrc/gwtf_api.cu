@@ -69,6 +69,16 @@ int exchange_sum(gwtf_exchange* x, double* data, int n, bool pdl, cudaStream_t s
     return 0;
 }
 
+// the same exchange as the tail of the kernel that completes `data` (tcgen05 layer kernels; gwtf_exchange.cuh)
+ExchangeTail make_tail(gwtf_exchange* x, double* data, int n) {
+    ExchangeTail t;
+    t.x.rank = x->rank; t.x.world = x->world; t.x.n = n; t.x.slot = x->slot; t.x.seq = ++x->seq; t.x.data = data;
+    t.x.timeout_ns = x->timeout_ns;
+    for (int r = 0; r < kMaxRanks; ++r) { t.x.recv[r] = x->recv[r]; t.x.flags[r] = x->flags[r]; }
+    return t;
+}
+ExchangeTail no_tail() { return ExchangeTail(); }
+
 int fwd_layer_dispatch(const LayerArgs& a, int phase, cudaStream_t st) {
     switch (fwd_engine(a.d)) {
         case kEngineFma: return a.seg ? fail(-4, "segmented rows need the tcgen05 forward") : launch_fwd_layer_fma(a, phase, st);
@@ -206,11 +216,11 @@ int gwtf_fwd_moments(const gwtf_stack_desc* desc, const float* points, int32_t B
 
 // NOTE: the C ABI takes explicit per-layer pointers so a multi-rank caller can all-reduce
 // mom / sum1 between phases; xin_shared=1 when `xin` is the (B,3,N) data cloud.
-int gwtf_fwd_layer_ex(const gwtf_stack_desc* desc, int32_t layer, int32_t phase, int32_t train, int32_t direct,
-                      const float* params, const float* bnbuf, const float* film, const float* xin,
-                      int32_t xin_shared, float* xout, float* ld, float* ssum, float* trio, float* y1out,
-                      const double* mom_in, double* mom_out, double* sum1, int32_t B, int32_t N, double n_total,
-                      void* stream) {
+static int fwd_layer_ex_impl(const gwtf_stack_desc* desc, int32_t layer, int32_t phase, int32_t train, int32_t direct,
+                             const float* params, const float* bnbuf, const float* film, const float* xin,
+                             int32_t xin_shared, float* xout, float* ld, float* ssum, float* trio, float* y1out,
+                             const double* mom_in, double* mom_out, double* sum1, int32_t B, int32_t N, double n_total,
+                             const ExchangeTail* tail, void* stream) {
     if (int rc = check_desc(desc)) return rc;
     if (layer < 0 || layer >= desc->n_layers) return fail(-12, "layer out of range");
     if (phase != 0 && phase != 1) return fail(-13, "phase must be 0 or 1");
@@ -224,12 +234,23 @@ int gwtf_fwd_layer_ex(const gwtf_stack_desc* desc, int32_t layer, int32_t phase,
     a.xin = xin; a.xin_shared = xin_shared; a.xout = xout; a.ld = ld; a.ssum = ssum; a.trio = trio; a.y1out = y1out;
     a.mom_in = mom_in; a.mom_out = mom_out; a.sum1 = sum1; a.B = B; a.N = N; a.n_total = n_total; a.tiles_per_shape = 0;
     a.seg = nullptr; a.seg_tiles = nullptr;
+    a.tail = tail ? *tail : no_tail();
     return fwd_layer_dispatch(a, phase, (cudaStream_t)stream);
 }
 
-int gwtf_fwd_layer(const gwtf_stack_desc* desc, int32_t layer, int32_t phase, int32_t train, const float* params,
-                   const float* bnbuf, const float* film, const float* points, float* ubuf, float* ld, float* ssum,
-                   float* ybuf, double* mom, double* sum1, int32_t B, int32_t N, double n_total, void* stream) {
+int gwtf_fwd_layer_ex(const gwtf_stack_desc* desc, int32_t layer, int32_t phase, int32_t train, int32_t direct,
+                      const float* params, const float* bnbuf, const float* film, const float* xin,
+                      int32_t xin_shared, float* xout, float* ld, float* ssum, float* trio, float* y1out,
+                      const double* mom_in, double* mom_out, double* sum1, int32_t B, int32_t N, double n_total,
+                      void* stream) {
+    return fwd_layer_ex_impl(desc, layer, phase, train, direct, params, bnbuf, film, xin, xin_shared, xout, ld, ssum, trio,
+                             y1out, mom_in, mom_out, sum1, B, N, n_total, nullptr, stream);
+}
+
+static int fwd_layer_impl(const gwtf_stack_desc* desc, int32_t layer, int32_t phase, int32_t train, const float* params,
+                          const float* bnbuf, const float* film, const float* points, float* ubuf, float* ld, float* ssum,
+                          float* ybuf, double* mom, double* sum1, int32_t B, int32_t N, double n_total,
+                          const ExchangeTail* tail, void* stream) {
     if (int rc = check_desc(desc)) return rc;
     if (!ubuf) return fail(-10, "null pointer argument");
     const int L = desc->n_layers, K = desc->n_components, F = desc->n_features;
@@ -241,9 +262,16 @@ int gwtf_fwd_layer(const gwtf_stack_desc* desc, int32_t layer, int32_t phase, in
     double* mom_out = (mom && layer > 0) ? mom + (size_t)(layer - 1) * K * GWTF_MOM_STRIDE : nullptr;
     double* s1 = sum1 ? sum1 + (size_t)layer * K * 4 * F : nullptr;
     float* y1 = ybuf ? ybuf + (size_t)layer * keep_layer_floats(*desc, B, N) : nullptr;
-    return gwtf_fwd_layer_ex(desc, layer, phase, train, 0, params, bnbuf, film, xin, first ? 1 : 0,
+    return fwd_layer_ex_impl(desc, layer, phase, train, 0, params, bnbuf, film, xin, first ? 1 : 0,
                              ubuf + (size_t)layer * slot, ld, ssum, nullptr, y1, mom_in, train ? mom_out : nullptr, s1,
-                             B, N, n_total, stream);
+                             B, N, n_total, tail, stream);
+}
+
+int gwtf_fwd_layer(const gwtf_stack_desc* desc, int32_t layer, int32_t phase, int32_t train, const float* params,
+                   const float* bnbuf, const float* film, const float* points, float* ubuf, float* ld, float* ssum,
+                   float* ybuf, double* mom, double* sum1, int32_t B, int32_t N, double n_total, void* stream) {
+    return fwd_layer_impl(desc, layer, phase, train, params, bnbuf, film, points, ubuf, ld, ssum, ybuf, mom, sum1, B, N,
+                          n_total, nullptr, stream);
 }
 
 int gwtf_fwd_bstat(const gwtf_stack_desc* desc, const float* params, const double* mom, const double* sum1,
@@ -352,15 +380,23 @@ static int fwd_all_impl(const gwtf_stack_desc* desc, int32_t train, const float*
         GWTF_CUDA(cudaMemsetAsync(sum1, 0, sizeof(double) * (size_t)L * K * 4 * F, st));
         if (int rc = gwtf_fwd_moments(desc, points, B, N, mom + (size_t)(L - 1) * K * GWTF_MOM_STRIDE, stream)) return rc;
     }
+    // tcgen05 kernels run the exchange of the sums they complete in their own tail (the statistics pass: sum1 of its
+    // layer, the apply pass: the moments of the next layer); the other engines get the stand-alone exchange kernel
+    const bool fold = ranks && fwd_engine(*desc) == kEngineTcFwd;
+    if (fold && K * 4 * F > x->slot) return fail(-20, "exchange slot too small for this stack");
     for (int l = L - 1; l >= 0; --l) {
         if (train) {
-            if (ranks) if (int rc = exchange_sum(x, mom + (size_t)l * K * GWTF_MOM_STRIDE, K * GWTF_MOM_STRIDE, pdl, st)) return rc;
-            if (int rc = gwtf_fwd_layer(desc, l, 0, 1, params, bnbuf, film, points, ubuf, ld, ssum, ybuf, mom, sum1, B,
-                                        N, n_total, stream)) return rc;
-            if (ranks) if (int rc = exchange_sum(x, sum1 + (size_t)l * K * 4 * F, K * 4 * F, pdl, st)) return rc;
+            if (ranks && (!fold || l == L - 1))
+                if (int rc = exchange_sum(x, mom + (size_t)l * K * GWTF_MOM_STRIDE, K * GWTF_MOM_STRIDE, pdl, st)) return rc;
+            ExchangeTail t0 = fold ? make_tail(x, sum1 + (size_t)l * K * 4 * F, K * 4 * F) : no_tail();
+            if (int rc = fwd_layer_impl(desc, l, 0, 1, params, bnbuf, film, points, ubuf, ld, ssum, ybuf, mom, sum1, B,
+                                        N, n_total, &t0, stream)) return rc;
+            if (ranks && !fold) if (int rc = exchange_sum(x, sum1 + (size_t)l * K * 4 * F, K * 4 * F, pdl, st)) return rc;
         }
-        if (int rc = gwtf_fwd_layer(desc, l, 1, train, params, bnbuf, film, points, ubuf, ld, ssum, ybuf, mom, sum1, B,
-                                    N, n_total, stream)) return rc;
+        ExchangeTail t1 = (fold && l > 0) ? make_tail(x, mom + (size_t)(l - 1) * K * GWTF_MOM_STRIDE, K * GWTF_MOM_STRIDE)
+                                          : no_tail();
+        if (int rc = fwd_layer_impl(desc, l, 1, train, params, bnbuf, film, points, ubuf, ld, ssum, ybuf, mom, sum1, B,
+                                    N, n_total, &t1, stream)) return rc;
     }
     if (train && bstat)
         if (int rc = gwtf_fwd_bstat(desc, params, mom, sum1, n_total, bstat, stream)) return rc;
@@ -396,10 +432,11 @@ int gwtf_bwd_seed(const gwtf_stack_desc* desc, const float* ubuf, const float* l
                            (cudaStream_t)stream);
 }
 
-int gwtf_bwd_layer(const gwtf_stack_desc* desc, int32_t layer, int32_t phase, int32_t train, const float* params,
-                   const float* bnbuf, const float* film, const float* points, const float* ubuf, const float* ybuf,
-                   const double* mom, const double* sum1, double* bsum, float* gbuf, const float* gs, float* dobuf,
-                   float* dparams, float* dfilm, int32_t B, int32_t N, double n_total, void* stream) {
+static int bwd_layer_impl(const gwtf_stack_desc* desc, int32_t layer, int32_t phase, int32_t train, const float* params,
+                          const float* bnbuf, const float* film, const float* points, const float* ubuf, const float* ybuf,
+                          const double* mom, const double* sum1, double* bsum, float* gbuf, const float* gs, float* dobuf,
+                          float* dparams, float* dfilm, int32_t B, int32_t N, double n_total, const ExchangeTail* tail,
+                          void* stream) {
     if (int rc = check_desc(desc)) return rc;
     const int L = desc->n_layers, K = desc->n_components, F = desc->n_features;
     if (layer < 0 || layer >= L) return fail(-12, "layer out of range");
@@ -425,12 +462,21 @@ int gwtf_bwd_layer(const gwtf_stack_desc* desc, int32_t layer, int32_t phase, in
     a.bsum_prev = (train && layer > 0) ? bsum + (size_t)(layer - 1) * K * 8 * F : nullptr;
     a.gbuf = gbuf; a.gs = gs; a.dobuf = dobuf; a.dparams = dparams; a.dfilm = dfilm;
     a.B = B; a.N = N; a.n_total = n_total; a.tiles_per_shape = 0;
+    a.tail = tail ? *tail : no_tail();
     cudaStream_t st = (cudaStream_t)stream;
     switch (bwd_engine(*desc)) {
         case kEngineFma: return launch_bwd_layer_fma(a, phase, st);
         case kEngineTc: a.y1in = nullptr; a.kept_y1 = 0; return launch_bwd_layer_tc(a, phase, st);
         default: return launch_bwd_layer_mma(a, phase, st);
     }
+}
+
+int gwtf_bwd_layer(const gwtf_stack_desc* desc, int32_t layer, int32_t phase, int32_t train, const float* params,
+                   const float* bnbuf, const float* film, const float* points, const float* ubuf, const float* ybuf,
+                   const double* mom, const double* sum1, double* bsum, float* gbuf, const float* gs, float* dobuf,
+                   float* dparams, float* dfilm, int32_t B, int32_t N, double n_total, void* stream) {
+    return bwd_layer_impl(desc, layer, phase, train, params, bnbuf, film, points, ubuf, ybuf, mom, sum1, bsum, gbuf, gs,
+                          dobuf, dparams, dfilm, B, N, n_total, nullptr, stream);
 }
 
 int gwtf_bwd_finish(const gwtf_stack_desc* desc, int32_t train, const float* params, const float* bnbuf,
@@ -465,13 +511,16 @@ static int bwd_all_impl(const gwtf_stack_desc* desc, int32_t train, const float*
     if (dnll) {   // seeds from the in-kernel NLL; otherwise gbuf / gs already hold dL/dz, dL/dS
         if (int rc = gwtf_bwd_seed(desc, ubuf, ld, base, logw, nll, dnll, B, N, gbuf, gs, dbase, dlogw, stream)) return rc;
     }
+    const bool fold = ranks && bwd_engine(*desc) == kEngineTc;     // the tcgen05 kernels exchange in their own tail
+    if (fold && K * 8 * F > x->slot) return fail(-20, "exchange slot too small for this stack");
     for (int l = 0; l < desc->n_layers; ++l)
         for (int phase = 0; phase < 2; ++phase) {
-            if (int rc = gwtf_bwd_layer(desc, l, phase, train, params, bnbuf, film, points, ubuf, ybuf, mom, sum1, bsum,
-                                        gbuf, gs, dobuf, dparams, dfilm, B, N, n_total, stream)) return rc;
             // phase 0 completes the sd1_bn sums (slots 0,1), phase 1 the bn0 sums (slots 2,3); the slots of
             // the other phase ride along (nobody reads slots 0,1 after phase 1)
-            if (ranks) if (int rc = exchange_sum(x, bsum + (size_t)l * K * 8 * F, K * 8 * F, pdl_on(*desc), (cudaStream_t)stream)) return rc;
+            ExchangeTail t = fold ? make_tail(x, bsum + (size_t)l * K * 8 * F, K * 8 * F) : no_tail();
+            if (int rc = bwd_layer_impl(desc, l, phase, train, params, bnbuf, film, points, ubuf, ybuf, mom, sum1, bsum,
+                                        gbuf, gs, dobuf, dparams, dfilm, B, N, n_total, &t, stream)) return rc;
+            if (ranks && !fold) if (int rc = exchange_sum(x, bsum + (size_t)l * K * 8 * F, K * 8 * F, pdl_on(*desc), (cudaStream_t)stream)) return rc;
         }
     return gwtf_bwd_finish(desc, train, params, bnbuf, mom, bsum, gbuf, points, dparams, dpoints, B, N, n_total, stream);
 }

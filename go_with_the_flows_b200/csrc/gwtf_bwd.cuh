@@ -2,6 +2,7 @@
 // (activations are recomputed from the saved layer inputs, never stored), closed-form finish.
 #pragma once
 #include "gwtf_common.cuh"
+#include "gwtf_exchange.cuh"
 #include "gwtf_mma.cuh"
 
 namespace gwtf {
@@ -75,6 +76,8 @@ struct BwdArgs {
     float* dfilm;            // layout of film (+=)
     int B, N, tiles_per_shape;
     double n_total;
+    // multi-rank train mode, tcgen05 kernels: the exchange of the sums this launch completes, run by its last CTA
+    ExchangeTail tail;
 };
 
 // (M, c) of the lazy bn0 correction for component j of layer `lc`:  G_in -= M x - c.

@@ -1,6 +1,7 @@
 // Forward kernels: fused eval-mode NLL, phased (batch-statistics) forward, NLL from state.
 #pragma once
 #include "gwtf_common.cuh"
+#include "gwtf_exchange.cuh"
 
 namespace gwtf {
 
@@ -170,6 +171,8 @@ struct LayerArgs {
     // seg_tiles[j][0..B] = exclusive prefix of the segments' 128-point tile counts.  Null = dense (K,B,3,N).
     const int32_t* seg;
     const int32_t* seg_tiles;
+    // multi-rank train mode, tcgen05 kernels: the exchange of the sums this launch completes, run by its last CTA
+    ExchangeTail tail;
 };
 
 template <int FP>

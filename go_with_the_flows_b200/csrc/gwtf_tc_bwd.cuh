@@ -923,6 +923,7 @@ __global__ void __launch_bounds__(PHASE == 0 ? kBwdDThreads : kBwdThreads, 1) k_
     GWTF_CLK_ZERO()
     if constexpr (PHASE == 0) bwd_tc_phase0<FPK, FPN>(a, smem_raw);
     else bwd_tc_phase1<FPK, FPN>(a, smem_raw);
+    exchange_tail(a.tail);
     GWTF_CLK_FLUSH()
 }
 

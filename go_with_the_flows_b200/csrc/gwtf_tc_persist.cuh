@@ -347,6 +347,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) k_fwd_layer_tcp(const Laye
         if (tid < 9) atomicAdd(&a.mom_out[j * GWTF_MOM_STRIDE + tid], S.dred[tid]);
     }
     if (warp == kSlots * 4) tmem_dealloc(tbase, 512);
+    exchange_tail(a.tail);
 }
 
 }  // namespace gwtf

@@ -187,10 +187,13 @@ int gwtf_bwd_all(const gwtf_stack_desc* desc, int32_t train, const float* params
 /* ---- several ranks (one process per GPU) sharing batch statistics: SyncBatchNorm semantics of the
  * reference's DistributedDataParallel training (train_ae.py:77-78, torch.nn.SyncBatchNorm.convert_sync_batchnorm)
  * The statistic sums of every layer phase are exchanged through NVLink peer memory by a push / flag /
- * add kernel (csrc/gwtf_exchange.cuh) instead of a collective call per phase.
+ * add step (csrc/gwtf_exchange.cuh) instead of a collective call per phase: the tcgen05 layer kernels run
+ * it in their own tail (the last CTA of the producing launch), the other engines in a one-CTA kernel.
  * gwtf_exchange_create : recv[r] / flags[r] = device pointers, valid on THIS device, to rank r's receive
- *                        buffer (2*world*slot_doubles doubles) and flag array (world uint64, zeroed before the
- *                        first exchange and never written by the host afterwards); symmetric / IPC memory.
+ *                        buffer (2*world*slot_doubles doubles) and flag array (32 uint64 -- entries [0, world)
+ *                        are the flags, entry 31 of the rank's own array is the library's last-CTA ticket --
+ *                        zeroed before the first exchange and never written by the host afterwards);
+ *                        symmetric / IPC memory.
  *                        timeout_s: seconds a rank waits for its peers before the exchange kernel gives up with
  *                        a (sticky) launch failure instead of hanging (<= 0: 600 s, NCCL-like).  All ranks must issue the same
  *                        sequence of exchanges; the handle owns the sequence counter, so one handle serves
