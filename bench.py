@@ -382,6 +382,13 @@ def rate(points_per_s, flops_per_pt, peaks, fma_peak, passes):
             'fma_peak': fma_peak, 'frac_of_fma_peak': ach / fma_peak, 'flops_per_point': flops_per_pt, 'traffic': None}
 
 
+def note(env, what):
+    """Progress line on stderr: a stalled multi-rank run shows where it stalled."""
+    if env.rank == 0:
+        sys.stderr.write('[bench] %s\n' % what)
+        sys.stderr.flush()
+
+
 def side_workloads(env, args, peaks, fma_peak):
     """The other BASELINE configs, on every rank, aggregated over ranks."""
     from go_with_the_flows_b200 import _native as nat
@@ -392,6 +399,7 @@ def side_workloads(env, args, peaks, fma_peak):
     out = {}
     quick = args.quick
 
+    note(env, 'side workload: eval_nll')
     # ---- eval-mode NLL, airplane model, 64 clouds per GPU: fp32-grade and single-pass TF32
     cfg, model = build_model('generative', dev)
     model.eval()
@@ -412,6 +420,7 @@ def side_workloads(env, args, peaks, fma_peak):
         stack.desc.eval_precision = flowstack._DEFAULTS['eval_precision']
     out['eval_nll'] = ev
 
+    note(env, 'side workload: sampling_c5')
     # ---- sampling sweep C5: airplane decoder, 256 latents per GPU
     fl_samp = L * 4 * (Fd * Fd + 3 * Fd)
     _, g2 = synthetic(256, 8, cfg['g_latent_space_size'], seed_shift=9 + rank)
@@ -441,6 +450,7 @@ def side_workloads(env, args, peaks, fma_peak):
     del model, stack
     torch.cuda.empty_cache()
 
+    note(env, 'side workload: sampling_c4')
     # ---- C4: config_SVR decoder (F=33, G=512, freevar), 256 x 2048 and 64 x 2500 (the config's cloud_size)
     cfg4, model4 = build_model('svr', dev)
     model4.eval()
@@ -466,6 +476,7 @@ def side_workloads(env, args, peaks, fma_peak):
     del model4, st4
     torch.cuda.empty_cache()
 
+    note(env, 'side workload: c3_step')
     # ---- C3: config_autoencoding train step, 128 clouds per GPU
     if not quick:
         cfg3, model3 = build_model('autoencoding', dev)
@@ -485,6 +496,7 @@ def side_workloads(env, args, peaks, fma_peak):
         del model3, st3, step3
         torch.cuda.empty_cache()
 
+    note(env, 'side workload: strong')
     # ---- strong scaling at the reference's semantics: 64 clouds in total (train_ae.py:77-78)
     if world > 1 and not quick:
         cfgs, models = build_model('generative', dev)
@@ -555,6 +567,7 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0 and os.environ.get('GWTF_BENCH_NO_SAMPLER') != '1':
         sampler.start()
+    note(env, 'timed steps')
     # ---- device-resident timing: K steps, each bracketed by CUDA events, L2 flushed in between
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     env.barrier()
@@ -567,6 +580,7 @@ def main():
     env.barrier()
     torch.cuda.profiler.stop()
     dev_ms = env.max_over_ranks(sum(e0.elapsed_time(e1) for e0, e1 in evs))
+    note(env, 'end-to-end steps')
     # ---- end to end: pinned host inputs -> public API -> loss on the host, wall clock
     env.barrier()
     t0 = time.perf_counter()

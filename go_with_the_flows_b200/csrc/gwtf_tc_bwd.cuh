@@ -16,7 +16,7 @@
 //   C2        dy0 = [y0 > 0] da0 -> TMEM operand; per-channel sums of dy0 (1, x_keep) by warp reduce-scatter
 //   batch D   du = dy0 Q0^T                (TS, N = 16): the input gradient
 // The two nets are processed one after the other (outer loop) so that one net's operands fit shared memory next to
-// the 128 KB of point-contraction operands, which the tile slots take turns on (sequence-numbered mbarrier).
+// the 128 KB of point-contraction operands, which the tile slots take turns on (a completion counter in shared memory).
 #pragma once
 #include "gwtf_tc_persist.cuh"
 #include "gwtf_bwd.cuh"
@@ -111,6 +111,22 @@ __shared__ unsigned int s_stage_clk[32];
 #define GWTF_CLK_FLUSH()
 #define GWTF_CLK_ZERO()
 #endif
+
+// Which slot takes which tile of a round (phase 1, two slots).  The point contractions of a CTA share one operand buffer
+// and are numbered in processing order; contraction k waits for the completion of k - 1 on an mbarrier by phase parity,
+// which is only unambiguous if the two slots strictly alternate.  Rounds can hold a single tile (a tile range starting at
+// an odd offset in its shape, a shape with an odd tile count), so the round's first tile goes to the slot whose turn it
+// is -- slot (seq & 1) -- not always to slot 0.
+struct SlotTurns {
+    int seq;                    // contractions of this CTA before the current round
+    // slot s in a round of `count` tiles: does it have a tile, which (offset in the round), and its sequence number
+    __device__ __forceinline__ bool take(int s, int count, int& off, int& my_seq) {
+        off = (s - seq) & 1;
+        my_seq = seq + off;
+        seq += count;
+        return off < count;
+    }
+};
 
 template <int FPK, int FPN>
 __device__ __forceinline__ void bwd_tc_phase1(const BwdArgs& a, unsigned char* smem_raw) {
@@ -215,17 +231,16 @@ __device__ __forceinline__ void bwd_tc_phase1(const BwdArgs& a, unsigned char* s
             // ================= MMA issuer of slot s =================
             const int s = warp - kBSlots * 4;
             if (elect_one()) {
-                int tiles_s = 0;
-                {
-                    RoundIter it(t_begin, t_end, tps, nullptr, B, kBSlots);
-                    int base, count, b;
-                    while (it.next(base, count, b)) tiles_s += (s < count) ? 1 : 0;
-                }
-                uint32_t req_phase = (uint32_t)((net * tiles_s * 4 + net) & 1);  // 4 requests per tile (+1 drain per net)
+                uint32_t req_phase = (uint32_t)(net & 1);        // 4 requests per tile and one drain per net
                 const uint32_t ts = tbase + s * C::SLOT;
                 const uint32_t tg = tbase + C::G + s * FPK;
+                SlotTurns turns{net * my_tiles};
+                RoundIter rounds(t_begin, t_end, tps, nullptr, B, kBSlots);
+                int rbase, rcount, rb;
 #pragma unroll 1
-                for (int t = 0; t < tiles_s; ++t) {
+                while (rounds.next(rbase, rcount, rb)) {
+                    int off, my_seq;
+                    if (!turns.take(s, rcount, off, my_seq)) continue;
                     mbar_wait(&S.req[s], req_phase); req_phase ^= 1u; tc_fence_after();
                     issue_ts<8, FPN>(ts + C::D, ts + C::Ahi, ts + C::Alo, S.B0.hi, S.B0.lo);
                     issue_ts<8, FPN>(ts + C::P, ts + C::Ahi, ts + C::Alo, S.PW.hi, S.PW.lo);
@@ -237,7 +252,7 @@ __device__ __forceinline__ void bwd_tc_phase1(const BwdArgs& a, unsigned char* s
                     issue_ts<FPK, FPN>(ts + C::Ahi, ts + C::D, ts + C::P, S.W1T.hi, S.W1T.lo);     // r lives in D | P
                     tc_commit(&S.done[s]);
                     issue_point_contraction<FPK>(tg, mn);
-                    tc_commit(&S.buf_free);
+                    tc_commit(&S.buf_free);                                     // contraction my_seq has consumed the buffer
                     mbar_wait(&S.req[s], req_phase); req_phase ^= 1u; tc_fence_after();
                     issue_ts<FPK, 16>(ts + C::Ahi, ts + C::D, ts + C::P, S.Q0.hi, S.Q0.lo);        // dy0 lives in D | P
                     tc_commit(&S.done[s]);
@@ -253,21 +268,15 @@ __device__ __forceinline__ void bwd_tc_phase1(const BwdArgs& a, unsigned char* s
             const uint32_t trow = tbase + slot * C::SLOT + lane_off;
             uint64_t* req = &S.req[slot];
             uint64_t* done = &S.done[slot];
-            // parities continue across the net loop: count what this slot did in the previous net
-            int tiles_s = 0;
-            {
-                RoundIter it0(t_begin, t_end, tps, nullptr, B, kBSlots);
-                int base, count, b;
-                while (it0.next(base, count, b)) tiles_s += (slot < count) ? 1 : 0;
-            }
-            uint32_t done_phase = (uint32_t)((net * tiles_s * 4 + net) & 1);
+            uint32_t done_phase = (uint32_t)(net & 1);           // 4 requests per tile and one drain per net
             auto request = [&]() { tc_fence_before(); mbar_arrive(req); };
             auto wait_done = [&]() { mbar_wait(done, done_phase); done_phase ^= 1u; tc_fence_after(); };
             // column sums of dy0 (1 | xa | xb): acc0 = channel `lane`, acc1 = channel 32 + (lane & 7)
             float acc0[3] = {0.f, 0.f, 0.f}, acc1[3] = {0.f, 0.f, 0.f};
             float* coltile = S.col[warp];
             int cur_b = -1;
-            int seq = net * my_tiles;              // sequence number of this CTA's point contractions (buffer turns)
+            SlotTurns turns{net * my_tiles};       // sequence numbers of this CTA's point contractions (buffer turns)
+            SlotTurns turns_ahead{net * my_tiles};
             GWTF_CLK_INIT(blockIdx.x == 0 && blockIdx.y == 0 && tid == 0)
             RoundIter it(t_begin, t_end, tps, nullptr, B, kBSlots);
             FilmAhead<FPN> film;
@@ -281,8 +290,10 @@ __device__ __forceinline__ void bwd_tc_phase1(const BwdArgs& a, unsigned char* s
                 int pbase, pcount, pb;
 #pragma unroll
                 for (int i = 0; i < 9; ++i) pf[i] = 0.f;
-                if (!ahead.next(pbase, pcount, pb) || slot >= pcount) return;
-                const int pn = (pbase + slot - ahead.shape_begin()) * 128 + wtid;
+                if (!ahead.next(pbase, pcount, pb)) return;
+                int poff, pseq;
+                if (!turns_ahead.take(slot, pcount, poff, pseq)) return;
+                const int pn = (pbase + poff - ahead.shape_begin()) * 128 + wtid;
                 if (pn >= N) return;
                 const float* pxin = a.xin_shared ? a.xin + (size_t)pb * 3 * N : a.xin + ((size_t)j * B + pb) * 3 * N;
                 const float* pdob = a.dobuf + ((size_t)j * B + pb) * 6 * N + (size_t)net * 3 * N;
@@ -339,10 +350,9 @@ __device__ __forceinline__ void bwd_tc_phase1(const BwdArgs& a, unsigned char* s
                     cur_b = b;
                     GWTF_CLK(12)
                 }
-                const int my_seq = seq + slot;
-                seq += count;
-                if (slot >= count) { prefetch(); continue; }
-                const int t = base + slot;
+                int off, my_seq;
+                if (!turns.take(slot, count, off, my_seq)) { prefetch(); continue; }
+                const int t = base + off;
                 const int n = (t - it.shape_begin()) * 128 + wtid;
                 const bool valid = n < N;
                 const size_t sb = ((size_t)j * B + b) * 3 * N;
@@ -423,6 +433,8 @@ __device__ __forceinline__ void bwd_tc_phase1(const BwdArgs& a, unsigned char* s
                     }
                     if (!have_turn) {
                         GWTF_CLK(4)
+                        // (contraction my_seq - 1 ran in the other slot -- SlotTurns -- and this slot's own my_seq - 2 is
+                        // complete, so the barrier is at most one phase away)
                         if (my_seq > 0) mbar_wait(&S.buf_free, (uint32_t)((my_seq - 1) & 1));
                         have_turn = true;
                         GWTF_CLK(5)

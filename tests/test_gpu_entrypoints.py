@@ -209,10 +209,12 @@ def test_c3_autoencoding_4x2048_against_fp64_oracle():
 
 
 # ------------------------------------------------------------------------------------------ ragged gradients
-@pytest.mark.parametrize('B,N', [(2, 1025), (2, 2500), (3, 130), (40, 2048)])
+@pytest.mark.parametrize('B,N', [(2, 1025), (2, 2500), (3, 130), (40, 2048), (7, 2048)])
 def test_train_mode_gradients_at_ragged_cloud_sizes(B, N):
-    """N not a multiple of 128 / 256 (config_SVR uses 2500), and a batch large enough that every persistent CTA walks
-    many tiles and several shapes (40 x 2048: 13 tiles per CTA): NLL and every gradient against the fp64 oracle."""
+    """N not a multiple of 128 / 256 (config_SVR uses 2500), a batch large enough that every persistent CTA walks
+    many tiles and several shapes (40 x 2048: 13 tiles per CTA), and one whose CTAs own 3 tiles each (7 x 2048 with
+    K = 3 on 148 SMs), so that tile ranges start at odd offsets inside a shape and the two-slot backward kernel runs
+    partial rounds: NLL and every gradient against the fp64 oracle."""
     from go_with_the_flows_b200.networks.losses import FlowMixtureNLL
     gd = Golden('small_c3_freevar')
     gen = torch.Generator().manual_seed(B * 7919 + N)
