@@ -19,6 +19,7 @@ struct gwtf_exchange {
     unsigned long long timeout_ns = 600ull * 1000000000ull;
     double* recv[kMaxRanks] = {};
     unsigned long long* flags[kMaxRanks] = {};
+    int ll = 1;                 // GWTF_EXCHANGE_LL=0: data -> fence -> flag protocol
 };
 
 namespace gwtf {
@@ -63,9 +64,9 @@ int exchange_sum(gwtf_exchange* x, double* data, int n, bool pdl, cudaStream_t s
     if (n > x->slot) return fail(-20, "exchange slot too small for this stack");
     ExchangeArgs a;
     a.rank = x->rank; a.world = x->world; a.n = n; a.slot = x->slot; a.seq = ++x->seq; a.data = data;
-    a.timeout_ns = x->timeout_ns;
+    a.timeout_ns = x->timeout_ns; a.ll = x->ll;
     for (int r = 0; r < kMaxRanks; ++r) { a.recv[r] = x->recv[r]; a.flags[r] = x->flags[r]; }
-    GWTF_CUDA(launch_pdl(pdl, k_exchange_sum, dim3(1), dim3(256), 0, st, a));
+    GWTF_CUDA(launch_pdl(pdl, k_exchange_sum, dim3(1), dim3(n > 512 ? 1024 : 256), 0, st, a));
     return 0;
 }
 
@@ -73,7 +74,7 @@ int exchange_sum(gwtf_exchange* x, double* data, int n, bool pdl, cudaStream_t s
 ExchangeTail make_tail(gwtf_exchange* x, double* data, int n) {
     ExchangeTail t;
     t.x.rank = x->rank; t.x.world = x->world; t.x.n = n; t.x.slot = x->slot; t.x.seq = ++x->seq; t.x.data = data;
-    t.x.timeout_ns = x->timeout_ns;
+    t.x.timeout_ns = x->timeout_ns; t.x.ll = x->ll;
     for (int r = 0; r < kMaxRanks; ++r) { t.x.recv[r] = x->recv[r]; t.x.flags[r] = x->flags[r]; }
     return t;
 }
@@ -340,6 +341,7 @@ int gwtf_exchange_create(int32_t rank, int32_t world, void* const* recv, void* c
     gwtf_exchange* x = new (std::nothrow) gwtf_exchange();
     if (!x) return fail(-26, "out of host memory");
     x->rank = rank; x->world = world; x->slot = slot_doubles;
+    if (const char* e = getenv("GWTF_EXCHANGE_LL")) x->ll = e[0] != '0';
     if (timeout_s > 0.0) x->timeout_ns = (unsigned long long)(timeout_s * 1e9);
     for (int r = 0; r < world && world > 1; ++r) {
         x->recv[r] = (double*)recv[r];

@@ -20,6 +20,7 @@ constexpr int kMaxRanks = 16;
 
 struct ExchangeArgs {
     int rank = 0, world = 0, n = 0, slot = 0; // n doubles to add up, slot = doubles per (parity, rank) slot
+    int ll = 0;                               // 1: 16-byte cells carrying their own sequence number (exchange_body_ll)
     unsigned long long seq = 0;
     unsigned long long timeout_ns = 0;        // how long to wait for the peers before giving up
     double* data = nullptr;                   // in: this rank's partial sums, out: the totals
@@ -59,10 +60,57 @@ __device__ __forceinline__ void exchange_body(const ExchangeArgs& a) {
     }
 }
 
-static __global__ void __launch_bounds__(256) k_exchange_sum(const ExchangeArgs a) {
+// Low-latency variant (the default): no separate flag, no system fence between data and flag.  Every double travels as
+// one 16-byte cell {lo32, seq32, hi32, seq32} written with a single vector store; each 8-byte half carries its own copy
+// of the (32-bit, non-zero) sequence number, so a reader that sees both copies has both halves -- the only atomicity
+// assumed of a peer store is 8 bytes (the scheme of NCCL's LL protocol).  The receive buffer then holds
+// [2][world][slot] cells = twice the bytes; parity double-buffering and the "at most one exchange ahead" argument are
+// unchanged.  One NVLink latency per exchange instead of data -> fence -> flag -> poll.
+__device__ __forceinline__ void exchange_body_ll(const ExchangeArgs& a) {
+    const int tid = threadIdx.x;
+    const size_t par = (size_t)(a.seq & 1ull);
+    const uint32_t tag = (uint32_t)a.seq;                      // never 0: sequence numbers start at 1, buffers at 0
+    for (int r = 0; r < a.world; ++r) {
+        uint4* dst = reinterpret_cast<uint4*>(a.recv[r]) + (par * a.world + a.rank) * a.slot;
+        for (int i = tid; i < a.n; i += blockDim.x) {
+            const unsigned long long v = (unsigned long long)__double_as_longlong(__ldcg(a.data + i));
+            const uint4 cell = make_uint4((uint32_t)v, tag, (uint32_t)(v >> 32), tag);
+            asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(dst + i), "r"(cell.x), "r"(cell.y),
+                         "r"(cell.z), "r"(cell.w) : "memory");
+        }
+    }
+    const uint4* in = reinterpret_cast<const uint4*>(a.recv[a.rank]) + par * a.world * a.slot;
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (int i = tid; i < a.n; i += blockDim.x) {
+        double s = 0.0;
+        for (int r = 0; r < a.world; ++r) {
+            const uint4* src = in + (size_t)r * a.slot + i;
+            uint4 c;
+            int spins = 0;
+            do {
+                asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(c.x), "=r"(c.y), "=r"(c.z), "=r"(c.w)
+                             : "l"(src) : "memory");
+                if (((++spins) & 1023) == 0) {
+                    unsigned long long t1;
+                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                    if (t1 - t0 > a.timeout_ns) __trap();       // a peer never showed up: fail (sticky error), do not hang
+                }
+            } while (c.y != tag || c.w != tag);
+            s += __longlong_as_double((long long)(((unsigned long long)c.z << 32) | c.x));
+        }
+        a.data[i] = s;
+    }
+}
+
+__device__ __forceinline__ void exchange_run(const ExchangeArgs& a) {
+    if (a.ll) exchange_body_ll(a); else exchange_body(a);
+}
+
+static __global__ void __launch_bounds__(1024) k_exchange_sum(const ExchangeArgs a) {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the consumer's prologue may overlap the exchange
     asm volatile("griddepcontrol.wait;" ::: "memory");                // the producer's sums are complete
-    exchange_body(a);
+    exchange_run(a);
 }
 
 // The same exchange folded into the tail of the kernel that produces the sums (the tcgen05 layer kernels): the last CTA
@@ -87,7 +135,7 @@ __device__ __forceinline__ void exchange_tail(const ExchangeTail& t) {
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    exchange_body(t.x);
+    exchange_run(t.x);
 }
 
 }  // namespace gwtf

@@ -91,7 +91,7 @@ def peer_exchange(slot_doubles, dev):
         import torch.distributed._symmetric_memory as symm
         slot = max(int(slot_doubles), 2048)
         head = 32                                   # doubles reserved for the flag array (>= world uint64)
-        buf = symm.empty(head + 2 * world * slot, dtype=torch.float64, device=dev)
+        buf = symm.empty(head + 4 * world * slot, dtype=torch.float64, device=dev)   # [2][world][slot] 16-byte cells
         buf.zero_()
         hdl = symm.rendezvous(buf, dist.group.WORLD)
         ptrs = [int(q) for q in hdl.buffer_ptrs]

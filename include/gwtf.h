@@ -190,7 +190,10 @@ int gwtf_bwd_all(const gwtf_stack_desc* desc, int32_t train, const float* params
  * add step (csrc/gwtf_exchange.cuh) instead of a collective call per phase: the tcgen05 layer kernels run
  * it in their own tail (the last CTA of the producing launch), the other engines in a one-CTA kernel.
  * gwtf_exchange_create : recv[r] / flags[r] = device pointers, valid on THIS device, to rank r's receive
- *                        buffer (2*world*slot_doubles doubles) and flag array (32 uint64 -- entries [0, world)
+ *                        buffer (4*world*slot_doubles doubles: [2][world][slot] 16-byte cells, each double with
+ *                        two copies of the exchange's sequence number -- no separate flag, no system fence on the
+ *                        critical path; GWTF_EXCHANGE_LL=0 selects the data / fence / flag protocol on the first
+ *                        half of the same buffer) and flag array (32 uint64 -- entries [0, world)
  *                        are the flags, entry 31 of the rank's own array is the library's last-CTA ticket --
  *                        zeroed before the first exchange and never written by the host afterwards);
  *                        symmetric / IPC memory.
