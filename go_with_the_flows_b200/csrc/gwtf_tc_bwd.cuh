@@ -16,7 +16,7 @@
 //   C2        dy0 = [y0 > 0] da0 -> TMEM operand; per-channel sums of dy0 (1, x_keep) by warp reduce-scatter
 //   batch D   du = dy0 Q0^T                (TS, N = 16): the input gradient
 // The two nets are processed one after the other (outer loop) so that one net's operands fit shared memory next to
-// the 128 KB of point-contraction operands, which the tile slots take turns on (a completion counter in shared memory).
+// the 128 KB of point-contraction operands, which the tile slots take turns on (one mbarrier; the slots strictly alternate, see SlotTurns).
 #pragma once
 #include "gwtf_tc_persist.cuh"
 #include "gwtf_bwd.cuh"
@@ -276,28 +276,25 @@ __device__ __forceinline__ void bwd_tc_phase1(const BwdArgs& a, unsigned char* s
             float* coltile = S.col[warp];
             int cur_b = -1;
             SlotTurns turns{net * my_tiles};       // sequence numbers of this CTA's point contractions (buffer turns)
-            SlotTurns turns_ahead{net * my_tiles};
             GWTF_CLK_INIT(blockIdx.x == 0 && blockIdx.y == 0 && tid == 0)
             RoundIter it(t_begin, t_end, tps, nullptr, B, kBSlots);
             FilmAhead<FPN> film;
             film.b = -1; film.s = 0.f; film.t = 0.f;
             if (t_begin < t_end) film.fetch(a.film, it.b, B, K, j, L, l, F, tid);
-            // a second iterator runs one round ahead: the global loads of the next tile (x, dO, incoming gradient) are in
-            // flight while this tile is processed
-            RoundIter ahead(t_begin, t_end, tps, nullptr, B, kBSlots);
+            // the global loads of this slot's next tile (x, dO, incoming gradient) are issued while the current tile is
+            // processed: within a shape that is tile t + 2.  The values carry the tile they belong to; at a shape boundary
+            // (or if the guess was wrong) the tile loads its own.
             float pf[9];
-            auto prefetch = [&]() {
-                int pbase, pcount, pb;
+            int pf_tile = -1;
+            auto fetch = [&](int tile, int bb, int shape_begin) {
+                pf_tile = tile;
 #pragma unroll
                 for (int i = 0; i < 9; ++i) pf[i] = 0.f;
-                if (!ahead.next(pbase, pcount, pb)) return;
-                int poff, pseq;
-                if (!turns_ahead.take(slot, pcount, poff, pseq)) return;
-                const int pn = (pbase + poff - ahead.shape_begin()) * 128 + wtid;
+                const int pn = (tile - shape_begin) * 128 + wtid;
                 if (pn >= N) return;
-                const float* pxin = a.xin_shared ? a.xin + (size_t)pb * 3 * N : a.xin + ((size_t)j * B + pb) * 3 * N;
-                const float* pdob = a.dobuf + ((size_t)j * B + pb) * 6 * N + (size_t)net * 3 * N;
-                const float* pg = a.gbuf + ((size_t)j * B + pb) * 3 * N;
+                const float* pxin = a.xin_shared ? a.xin + (size_t)bb * 3 * N : a.xin + ((size_t)j * B + bb) * 3 * N;
+                const float* pdob = a.dobuf + ((size_t)j * B + bb) * 6 * N + (size_t)net * 3 * N;
+                const float* pg = a.gbuf + ((size_t)j * B + bb) * 3 * N;
 #pragma unroll
                 for (int d = 0; d < 3; ++d) {
                     pf[d] = pxin[(size_t)d * N + pn];
@@ -305,7 +302,6 @@ __device__ __forceinline__ void bwd_tc_phase1(const BwdArgs& a, unsigned char* s
                     pf[6 + d] = pg[(size_t)d * N + pn];
                 }
             };
-            prefetch();
             int base, count, b;
             while (it.next(base, count, b)) {
                 if (b != cur_b) {
@@ -351,8 +347,9 @@ __device__ __forceinline__ void bwd_tc_phase1(const BwdArgs& a, unsigned char* s
                     GWTF_CLK(12)
                 }
                 int off, my_seq;
-                if (!turns.take(slot, count, off, my_seq)) { prefetch(); continue; }
+                if (!turns.take(slot, count, off, my_seq)) continue;
                 const int t = base + off;
+                if (pf_tile != t) fetch(t, b, it.shape_begin());
                 const int n = (t - it.shape_begin()) * 128 + wtid;
                 const bool valid = n < N;
                 const size_t sb = ((size_t)j * B + b) * 3 * N;
@@ -472,7 +469,7 @@ __device__ __forceinline__ void bwd_tc_phase1(const BwdArgs& a, unsigned char* s
                 request();                                              // -> batch C: da0, then dW1 += r^T a0
                 // (the proxy fence above is a MEMBAR.ALL.CTA in SASS and would wait for these loads: issue them after it,
                 // with the rest of the tile to land in)
-                prefetch();
+                if (t + 2 < min(it.shape_begin() + tps, t_end)) fetch(t + 2, b, it.shape_begin());
                 wait_done();                                            // (da0 only: dW1 keeps running)
                 GWTF_CLK(7)
                 {
