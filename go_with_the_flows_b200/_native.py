@@ -65,6 +65,7 @@ _SIGNATURES = {
     'gwtf_sample': [_D, c_f, c_f, c_f, c_f, c_f, c_i, c_i, c_u64, ctypes.c_uint32, c_f, c_f,
                     c_f, c_f, c_f, c_f],
     'gwtf_adam_step': [c_f, c_f, c_f, c_f, c_f, c_i64, c_d, c_d, c_d, c_d, c_d, c_i64, c_f],
+    'gwtf_debug_tile_schedule': [c_i, c_i, c_i, c_i, c_f, c_f, c_f],
 }
 _RESTYPES = {
     'gwtf_last_error_string': ([], ctypes.c_char_p),

@@ -33,6 +33,38 @@ int launch_bwd_layer_tc(const BwdArgs& a, int phase, cudaStream_t st) {
 
 }  // namespace gwtf
 
+// Host-side replay of the tile schedule of the persistent layer kernels (the same RoundIter / SlotTurns code the
+// kernels run): which CTA, tile slot and per-CTA sequence number every 128-point tile of a launch gets.
+extern "C" int gwtf_debug_tile_schedule(int32_t total_tiles, int32_t tiles_per_shape, int32_t grid_x, int32_t slots,
+                                        int32_t* tile_cta, int32_t* tile_slot, int32_t* tile_seq) {
+    using namespace gwtf;
+    if (total_tiles < 0 || tiles_per_shape < 1 || grid_x < 1 || slots < 1 || !tile_cta || !tile_slot || !tile_seq)
+        return fail(-10, "bad tile schedule query");
+    const int B = (total_tiles + tiles_per_shape - 1) / tiles_per_shape;
+    const int per_cta = (total_tiles + grid_x - 1) / grid_x;
+    int assigned = 0;
+    for (int cta = 0; cta < grid_x; ++cta) {
+        const int t_begin = min(cta * per_cta, total_tiles), t_end = min(t_begin + per_cta, total_tiles);
+        for (int s = 0; s < slots; ++s) {
+            RoundIter it(t_begin, t_end, tiles_per_shape, nullptr, B, slots);
+            SlotTurns turns{0};
+            int base, count, b, seq = 0;
+            while (it.next(base, count, b)) {
+                int off = s, my_seq = seq + s;
+                bool mine = s < count;
+                if (slots == kBSlots) mine = turns.take(s, count, off, my_seq);        // backward phase 1: strict alternation
+                seq += count;
+                if (!mine) continue;
+                const int t = base + off;
+                if (t < t_begin || t >= t_end || t / tiles_per_shape != b) return fail(-27, "tile outside its range or shape");
+                tile_cta[t] = cta; tile_slot[t] = s; tile_seq[t] = my_seq;
+                ++assigned;
+            }
+        }
+    }
+    return assigned;
+}
+
 #ifdef GWTF_STAGE_CLOCKS
 extern "C" int gwtf_debug_stage_clocks(unsigned long long* out, int reset) {
     cudaDeviceSynchronize();

@@ -120,7 +120,7 @@ __shared__ unsigned int s_stage_clk[32];
 struct SlotTurns {
     int seq;                    // contractions of this CTA before the current round
     // slot s in a round of `count` tiles: does it have a tile, which (offset in the round), and its sequence number
-    __device__ __forceinline__ bool take(int s, int count, int& off, int& my_seq) {
+    __host__ __device__ __forceinline__ bool take(int s, int count, int& off, int& my_seq) {
         off = (s - seq) & 1;
         my_seq = seq + off;
         seq += count;

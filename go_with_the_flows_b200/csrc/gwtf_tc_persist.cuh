@@ -53,14 +53,14 @@ struct RoundIter {
     int t, t_end, tps;
     const int32_t* pre;          // null = dense
     int b, s_begin, s_end, slots;
-    __device__ __forceinline__ RoundIter(int t0, int t1, int tps_, const int32_t* pre_, int B, int slots_ = kSlots)
+    __host__ __device__ __forceinline__ RoundIter(int t0, int t1, int tps_, const int32_t* pre_, int B, int slots_ = kSlots)
         : t(t0), t_end(t1), tps(tps_), pre(pre_), slots(slots_) {
         if (!pre) { b = t0 / tps; s_begin = b * tps; s_end = s_begin + tps; return; }
         int lo = 0, hi = B;                  // largest b with pre[b] <= t0
         while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (pre[mid] <= t0) lo = mid; else hi = mid; }
         b = lo; s_begin = pre[lo]; s_end = pre[lo + 1];
     }
-    __device__ __forceinline__ bool next(int& base, int& count, int& bb) {
+    __host__ __device__ __forceinline__ bool next(int& base, int& count, int& bb) {
         if (t >= t_end) return false;
         while (t >= s_end) { ++b; s_begin = s_end; s_end = pre ? pre[b + 1] : s_end + tps; }
         const int ti = t - s_begin;
@@ -72,7 +72,7 @@ struct RoundIter {
         t = end;
         return true;
     }
-    __device__ __forceinline__ int shape_begin() const { return s_begin; }
+    __host__ __device__ __forceinline__ int shape_begin() const { return s_begin; }
 };
 
 // PASSES: 3 = fp32-grade 3xTF32 (training, anything that feeds gradients), 1 = single-pass TF32 for the

@@ -590,17 +590,20 @@ def _batch_norm_train(H, weight, bias, sync):
 class _SyncBN(torch.autograd.Function):
     @staticmethod
     def forward(ctx, H, weight, bias):
-        stats = torch.cat([H.sum(0), (H * H).sum(0), H.new_full((1,), float(H.shape[0]))])
+        # sums in fp64: E[x^2] - mean^2 of fp32 sums loses the variance of channels whose mean dominates
+        Hd = H.double()
+        stats = torch.cat([Hd.sum(0), (Hd * Hd).sum(0), Hd.new_full((1,), float(H.shape[0]))])
         dist.all_reduce(stats)
         C = H.shape[1]
-        n = stats[-1]
-        mean = stats[:C] / n
-        var = (stats[C:2 * C] / n - mean * mean).clamp_min(0)
+        nd = stats[-1]
+        mean_d = stats[:C] / nd
+        var_d = (stats[C:2 * C] / nd - mean_d * mean_d).clamp_min(0)
+        mean, var, n = mean_d.to(H.dtype), var_d.to(H.dtype), nd.to(H.dtype)
         istd = torch.rsqrt(var + BN_EPS)
         xhat = (H - mean) * istd
         ctx.save_for_backward(xhat, weight, istd, n)
         ctx.mark_non_differentiable(mean, var)
-        return xhat * weight + bias, mean, var * (n / (n - 1).clamp_min(1))
+        return xhat * weight + bias, mean, (var_d * (nd / (nd - 1).clamp_min(1))).to(H.dtype)
 
     @staticmethod
     def backward(ctx, dy, _dm, _dv):

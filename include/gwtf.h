@@ -253,6 +253,15 @@ int gwtf_sample_layers(const gwtf_stack_desc* desc, const float* params, const f
 int gwtf_adam_step(float* p, const float* g, float* exp_avg, float* exp_avg_sq, float* max_exp_avg_sq, int64_t n,
                    double lr, double beta1, double beta2, double eps, double weight_decay, int64_t step, void* stream);
 
+/* ---- diagnostics (host only, no GPU needed): replay of the tile schedule of the persistent layer kernels -- the
+ * same code the kernels run.  For a launch of `total_tiles` 128-point tiles (`tiles_per_shape` per shape) on
+ * `grid_x` CTAs per component with `slots` tiles in flight per CTA (4: forward and backward phase 0, 2: backward
+ * phase 1), writes for every tile its CTA, tile slot and sequence number within the CTA; returns the number of
+ * tiles assigned (== total_tiles) or a negative error.  In the two-slot kernel consecutive sequence numbers of a
+ * CTA must belong to different slots (they take turns on one operand buffer); tests/test_dropin_cpu.py checks it. */
+int gwtf_debug_tile_schedule(int32_t total_tiles, int32_t tiles_per_shape, int32_t grid_x, int32_t slots,
+                             int32_t* tile_cta, int32_t* tile_slot, int32_t* tile_seq);
+
 #ifdef __cplusplus
 }
 #endif

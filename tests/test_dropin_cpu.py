@@ -156,3 +156,39 @@ def test_cabi_host_side_queries_without_a_gpu():
     assert lib.gwtf_exchange_create(0, 4, None, None, 0, 0.0, ctypes.byref(out)) != 0   # several ranks need peer buffers
     assert lib.gwtf_exchange_create(5, 4, None, None, 0, 0.0, ctypes.byref(out)) != 0
     assert b'rank' in lib.gwtf_last_error_string()
+
+
+@pytest.mark.parametrize('slots', [2, 4])
+def test_tile_schedule_of_the_persistent_kernels(slots):
+    """Host replay of the kernels' own tile scheduling code (gwtf_debug_tile_schedule): over launch shapes that give
+    CTAs odd tile counts, tile ranges starting mid-shape and shapes with odd tile counts, every tile is processed
+    exactly once, by the CTA that owns its range; and in the two-slot backward kernel consecutive point
+    contractions of a CTA always belong to different slots (they take turns on one operand buffer by mbarrier
+    phase parity -- two in a row in one slot is the deadlock of 16 clouds x 2048 points on 148 SMs)."""
+    import ctypes
+    import numpy as np
+    from go_with_the_flows_b200 import _native as nat
+    lib = nat.lib()
+    rng = np.random.RandomState(7 + slots)
+    cases = [(16, 16, 37), (24, 16, 37), (5, 16, 37), (64, 16, 37), (7, 16, 49), (2, 9, 9), (13, 20, 37), (3, 2, 3),
+             (9, 1, 5), (40, 16, 37), (1, 16, 8), (11, 3, 37)]
+    cases += [(int(rng.randint(1, 70)), int(rng.randint(1, 24)), int(rng.randint(1, 75))) for _ in range(60)]
+    for B, tps, gx_max in cases:
+        total = B * tps
+        gx = max(1, min(gx_max, (total + slots - 1) // slots))           # the launchers' grid rule
+        cta = np.full(total, -1, np.int32)
+        slot = np.full(total, -1, np.int32)
+        seq = np.full(total, -1, np.int32)
+        ptr = lambda a: a.ctypes.data_as(ctypes.c_void_p)                # noqa: E731
+        n = lib.gwtf_debug_tile_schedule(total, tps, gx, slots, ptr(cta), ptr(slot), ptr(seq))
+        assert n == total, (B, tps, gx, n, lib.gwtf_last_error_string())
+        assert (cta >= 0).all() and (slot >= 0).all() and (slot < slots).all()
+        per = (total + gx - 1) // gx
+        assert (cta == np.arange(total) // per).all()                    # contiguous ranges
+        for c in range(gx):
+            idx = np.nonzero(cta == c)[0]
+            if slots == 2 and len(idx):
+                order = idx[np.argsort(seq[idx])]
+                assert (np.sort(seq[idx]) == np.arange(len(idx))).all(), (B, tps, gx, c)
+                assert (slot[order] == np.arange(len(idx)) % 2).all(), (B, tps, gx, c, slot[order])
+                assert (order == idx).all()                              # contractions run in tile order
