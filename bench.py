@@ -15,6 +15,7 @@ per GPU (weak scaling), random init (seed 0), synthetic clouds N(0, 0.2^2), late
 train step) with the aggregate over ranks and its own roofline:
   eval_nll      C1-shaped eval-mode NLL (fp32-grade and the single-pass TF32 tier)
   c3_step       config_autoencoding.yaml (F=33, G=512, freevar) train step
+  small_step    C2 model at 4 clouds x 2048 per GPU: the launch-bound regime
   strong        C2 at the reference's semantics: 64 clouds in total, 64/N per GPU (train_ae.py:77-78)
   sampling_c4   config_SVR.yaml decoder: 256 latents x 2048 points and 64 x 2500
   sampling_c5   sweep 2k / 16k / 128k / 1M points x 256 latents, airplane decoder
@@ -494,6 +495,23 @@ def side_workloads(env, args, peaks, fma_peak):
                           'workload': 'config_autoencoding (K=4,L=33,F=33,G=512,freevar), train-mode fwd+bwd',
                           'roofline': rate(pps / world, fl3, peaks, fma_peak, 3)}
         del model3, st3, step3
+        torch.cuda.empty_cache()
+
+    note(env, 'side workload: small_step')
+    # ---- small-batch train step (4 clouds x 2048 per GPU): launch-bound regime, 132 layer launches of ~10 us each
+    if not quick:
+        cfg4, model4 = build_model('generative', dev)
+        model4.train()
+        model4.mode = 'training'
+        B4 = 4
+        p4, g4 = synthetic(B4, N, cfg4['g_latent_space_size'], seed_shift=29 + rank)
+        p4, g4 = p4.to(dev), g4.to(dev)
+        step4 = make_step(model4, world, N)
+        ms = env.timed(lambda: step4(p4, g4), reps=10, warmup=3, flush=False)
+        out['small_step'] = {'ms_per_step': ms, 'points_per_s': world * B4 * N / (ms * 1e-3), 'clouds_per_gpu': B4,
+                             'workload': 'airplane model, train-mode fwd+bwd, 4 clouds x 2048 per GPU (CUDA events '
+                                         'around the whole step incl. the PyTorch launches of the FiLM nets)'}
+        del model4, step4
         torch.cuda.empty_cache()
 
     note(env, 'side workload: strong')
