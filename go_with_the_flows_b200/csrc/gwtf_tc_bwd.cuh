@@ -4,7 +4,8 @@
 // Same BwdArgs and outputs as the mma.sync kernels (gwtf_bwd_mma.cuh); math: SURVEY.md App. F.
 //
 // Phase 1 (k_bwd_layer_tc<.., 1>), per 128-point tile and net -- every contraction is a UMMA chain, 3xTF32:
-//   batch A   y0 = X B0^T                  (SS, K = 8: the (x,1 | dO) operand row of every point)
+//   batch A   y0 = X B0^T                  (TS, K = 8: the (x,1 | dO) operand row of every point, written to the TMEM
+//                                           columns a0 takes over afterwards: no shared-memory write, no proxy fence)
 //             P  = X PW^T                  dO (alpha W2): the sd2 backward with s/sigma1 folded in
 //   C0        a0 = relu(y0) -> TMEM operand (hi | lo), [y0 > 0] kept as a bit mask
 //   batch B   y1 = a0 B1^T                 (TS) sd1 + BN1 + FiLM folded into B1 (bias column): y1 leaves finished
@@ -13,10 +14,12 @@
 //   batch C   da0 = r W1                   (TS)
 //             dW1 += r^T a0                (SS, K = the tile's 128 points, M = 64, accumulator resident in TMEM for the
 //                                           whole kernel; committed separately so the tile goes on while it runs)
-//   C2        dy0 = [y0 > 0] da0 -> TMEM operand; per-channel sums of dy0 (1, x_keep) by warp reduce-scatter
+//   C2        dy0 = [y0 > 0] da0 -> TMEM operand; per-channel sums of dy0 (1, x_keep) as column sums through the warp's
+//             shared-memory tile (gwtf_tc_fwd.cuh: col_write_row)
 //   batch D   du = dy0 Q0^T                (TS, N = 16): the input gradient
 // The two nets are processed one after the other (outer loop) so that one net's operands fit shared memory next to
-// the 128 KB of point-contraction operands, which the tile slots take turns on (one mbarrier; the slots strictly alternate, see SlotTurns).
+// the 80 KB of point-contraction operands, which the tile slots take turns on (one mbarrier; the slots strictly
+// alternate, see SlotTurns).
 #pragma once
 #include "gwtf_tc_persist.cuh"
 #include "gwtf_bwd.cuh"
@@ -589,7 +592,7 @@ __device__ __forceinline__ void bwd_tc_phase1(const BwdArgs& a, unsigned char* s
 // Per tile and net (logvar net first: its head fixes sigma, hence dO of both nets):
 //   batch A   y0 = X B0^T  ->  a0 = relu(y0)                      batch B   y1 = a0 B1^T  (folded)
 //   logvar net only:  a1 = relu(y1) -> batch C   o = a1 B2^T (N = 16)  -> softsign / sigma / dO, written to dobuf, gbuf
-//   sums over points of dO_d a1 and dO_d [y1 > 0] for the warped dims d (warp reduce-scatter, per-shape accumulators):
+//   sums over points of dO_d a1 and dO_d [y1 > 0] for the warped dims d (column sums through the warp's tile, per-shape accumulators):
 //     dW2 = sum dO a1;   dt = sum_d W2_d sum dO_d [y1>0];   ds = (sum_d W2_d sum dO_d a1 - t dt) / s     (a1 = [y1>0] y1)
 //   so the CUDA cores never form da1 = W2^T dO per point and never touch a per-channel constant in the tile loop.
 // =============================================================================================

@@ -1,12 +1,12 @@
 // Persistent, warp-specialised tcgen05 forward of one coupling layer.
 //
 // One CTA per SM: 4 compute warpgroups (128 threads = 128 TMEM lanes each, one 128-point tile in flight
-// per warpgroup, 128 TMEM columns per slot) + 1 MMA-issuer warp.  The warpgroups never synchronise with
-// each other on the hot path: a warpgroup hands its operands to the issuer through an mbarrier
-// (`req[s]`, 128 arrivals) and sleeps on `done[s]`, which the issuer's tcgen05.commit completes.  The
-// each slot has its own issuer warp (a single thread tops out at one small UMMA per ~45 cycles, half the
-// tensor rate at N = 48), so the tensor pipe works on whichever tiles are ready while the other
-// warpgroups run their relu / split / statistics on the CUDA cores.
+// per warpgroup, 128 TMEM columns per slot) + one MMA-issuer warp per slot.  The warpgroups never synchronise
+// with each other on the hot path (only at a shape boundary, to restage the per-shape operands): a warpgroup
+// hands its operands to its issuer through an mbarrier (`req[s]`, 128 arrivals) and sleeps on `done[s]`, which
+// the issuer's tcgen05.commit completes, so the tensor pipe works on whichever tiles are ready while the other
+// warpgroups run their relu / split / statistics on the CUDA cores.  The issuer is one ELECTED thread
+// (elect.sync) working from warp-uniform values: it then issues tcgen05.mma back to back at the pipe's rate.
 // Same math and operand layouts as gwtf_tc_fwd.cuh (all-GEMM chain MMA0 -> relu -> MMA1 -> relu -> MMA2).
 #pragma once
 #include "gwtf_tc_fwd.cuh"
